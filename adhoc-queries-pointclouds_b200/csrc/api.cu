@@ -1,0 +1,1209 @@
+// api.cu — C ABI of libpcq: device context, files resident in HBM, device-resident collectors and
+// the orchestration of one Searcher::search_file batch (searcher.rs:24-31; main.rs:122-183).
+//
+// Host work per call is O(files): validate like the reference does before its per-point loop
+// (las.rs:59-99, 199-219; last.rs:53-109, 220-250), build one Segment per file, upload the table,
+// launch ONE kernel for the whole batch.  All per-point work is in kernels.cu; there is no CPU scan.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "host_logic.hpp"
+#include "pcq_device.h"
+
+using namespace pcq;
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) return fail(PCQ_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define RC(call)             \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != PCQ_OK) return rc_; \
+  } while (0)
+
+namespace {
+
+constexpr int kUploadSlots = 8;
+constexpr int kChunkBuffers = 3;
+
+struct UploadSlot {
+  void* host = nullptr;
+  void* dev = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
+
+// device-side scalars of one collector
+struct DevBlock {
+  unsigned long long count;       // matches (COUNT / BUFFER)
+  unsigned long long cand_count;  // GRID: candidates appended (may exceed capacity on overflow)
+  unsigned long long out_count;   // GRID finalisation: winners emitted
+  uint32_t flags;
+  uint32_t pad_;
+};
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct pcq_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int variant = 0;
+  uint64_t launches = 0;
+  UploadSlot slots[kUploadSlots];
+  int next_slot = 0;
+  // MODE_SELECT scratch
+  unsigned long long* tile_state = nullptr;  // [0] = ticket, [1..] = descriptors
+  uint64_t tile_state_cap = 0;
+  // GRID finalisation scratch (one finalisation at a time)
+  unsigned long long* idx_scratch = nullptr;
+  uint64_t idx_scratch_cap = 0;
+  unsigned long long* part_scratch = nullptr;  // 2 * n_parts counters
+  uint32_t part_scratch_cap = 0;
+  // host-staged streaming
+  cudaStream_t copy_stream = nullptr;
+  void* chunk[kChunkBuffers] = {nullptr, nullptr, nullptr};
+  size_t chunk_cap = 0;
+  cudaEvent_t chunk_copied[kChunkBuffers] = {nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_free[kChunkBuffers] = {nullptr, nullptr, nullptr};
+};
+
+struct pcq_file {
+  pcq_ctx* ctx = nullptr;
+  pcq_file_desc desc{};
+  uint8_t raw_format = 0;
+  uint64_t first_point = 0;  // index inside the file of record 0 of this range
+  uint64_t n_points = 0;     // points in this range
+  void* owned = nullptr;     // device allocation owned by this object (staged files)
+  const uint8_t* rec = nullptr;
+  const uint8_t* cls = nullptr;
+  const uint8_t* rgb = nullptr;
+  bool has_scan_base = false;
+  uint64_t scan_base = 0;
+};
+
+struct pcq_collector {
+  pcq_ctx* ctx = nullptr;
+  int kind = 0;
+  DevBlock* dev = nullptr;
+  uint64_t scan_total = 0;  // points of all files fed so far (scan index of the next file)
+  // BUFFER
+  uint8_t* d_out = nullptr;
+  uint64_t out_len = 0, out_cap = 0;
+  // GRID
+  double gmin[3]{}, gmax[3]{}, cell = 0;
+  uint64_t dims[3]{}, bits[3]{};
+  GridDev grid{};
+  uint64_t cand_len = 0;
+  uint8_t* d_final = nullptr;
+  uint64_t final_cap = 0, final_n = 0;
+  bool final_valid = false;
+  // export scratch
+  Candidate* d_export = nullptr;
+  uint64_t export_cap = 0;
+  // host copy of points()
+  void* h_pts = nullptr;
+  uint64_t h_cap = 0;
+};
+
+namespace {
+
+int use_device(pcq_ctx* ctx) {
+  CU(cudaSetDevice(ctx->device));
+  return PCQ_OK;
+}
+
+// copy a small parameter table to the device through a ring of pinned slots (fully asynchronous)
+int upload(pcq_ctx* ctx, const void* src, size_t bytes, void** dev_out) {
+  UploadSlot& s = ctx->slots[ctx->next_slot];
+  ctx->next_slot = (ctx->next_slot + 1) % kUploadSlots;
+  if (s.pending) {
+    CU(cudaEventSynchronize(s.ev));
+    s.pending = false;
+  }
+  if (s.cap < bytes) {
+    if (s.host) cudaFreeHost(s.host);
+    if (s.dev) cudaFree(s.dev);
+    s.host = s.dev = nullptr;
+    s.cap = 0;
+    size_t cap = round_up(std::max<size_t>(bytes, 16384), 4096);
+    CU(cudaMallocHost(&s.host, cap));
+    CU(cudaMalloc(&s.dev, cap));
+    s.cap = cap;
+  }
+  if (!s.ev) CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  std::memcpy(s.host, src, bytes);
+  CU(cudaMemcpyAsync(s.dev, s.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(s.ev, ctx->stream));
+  s.pending = true;
+  *dev_out = s.dev;
+  return PCQ_OK;
+}
+
+int read_devblock(pcq_collector* c, DevBlock* out) {
+  CU(cudaMemcpyAsync(out, c->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, c->ctx->stream));
+  CU(cudaStreamSynchronize(c->ctx->stream));
+  return PCQ_OK;
+}
+
+int layout_of_ext(const char* ext) {
+  if (!ext) return -1;
+  if (std::strcmp(ext, "las") == 0) return PCQ_LAYOUT_LAS;
+  if (std::strcmp(ext, "last") == 0) return PCQ_LAYOUT_LAST;
+  return -1;
+}
+
+uint32_t cls_offset_in_record(uint8_t format) { return format <= 5 ? 15u : 16u; }  // las.rs:202-205, last.rs:69-71
+int rgb_offset_in_record(uint8_t format) {                                         // las.rs:38-45
+  switch (format) {
+    case 2: return 20;
+    case 3: return 28;
+    case 5: return 28;
+    default: return -1;
+  }
+}
+
+uint8_t field_alignment(const void* base, uint32_t stride) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+  if ((a & 3u) == 0 && (stride & 3u) == 0) return 4;
+  if ((a & 1u) == 0 && (stride & 1u) == 0) return 2;
+  return 1;
+}
+
+struct SegmentPlan {
+  bool skip = false;  // file cannot contribute (early-out of las.rs:82-84 or empty integer range)
+  int32_t lo[3]{}, hi[3]{};
+};
+
+// Everything the reference does between opening a file and entering its per-point loop.
+int plan_file(const pcq_file_desc& d, uint8_t raw_format, const pcq_query* q, SegmentPlan* plan) {
+  plan->skip = false;
+  if (q->kind == PCQ_QUERY_BOUNDS) {
+    // neither bounds search masks the format byte (las.rs:59-60, last.rs:53-54)
+    if (raw_format > 10) return fail(PCQ_ERR_FORMAT, "Invalid LAS format %u", raw_format);
+    int hit = 0;
+    RC(file_intersects(&d, q->qmin, q->qmax, &hit));
+    if (!hit) {
+      plan->skip = true;
+      return PCQ_OK;
+    }
+    int64_t lo[3], hi[3];
+    RC(local_bounds(&d, q->qmin, q->qmax, lo, hi));
+    for (int i = 0; i < 3; ++i) {
+      if (lo[i] > INT32_MAX || hi[i] < INT32_MIN) plan->skip = true;  // no i32 coordinate can match
+      plan->lo[i] = (int32_t)std::max<int64_t>(lo[i], INT32_MIN);
+      plan->hi[i] = (int32_t)std::min<int64_t>(hi[i], INT32_MAX);
+    }
+    return PCQ_OK;
+  }
+  if (q->kind == PCQ_QUERY_CLASS) {
+    // LAS class search does not mask (las.rs:199-212); LAST class search does (last.rs:222)
+    if (d.layout == PCQ_LAYOUT_LAS && raw_format > 10) return fail(PCQ_ERR_FORMAT, "Invalid LAS format %u", raw_format);
+    return PCQ_OK;
+  }
+  return fail(PCQ_ERR_ARG, "unknown query kind %u", q->kind);
+}
+
+void fill_segment(Segment* s, const pcq_file_desc& d, const uint8_t* rec, const uint8_t* cls, const uint8_t* rgb,
+                  uint64_t n_points, const SegmentPlan& plan, uint32_t lane, uint64_t scan_base) {
+  std::memset(s, 0, sizeof(*s));
+  s->rec = rec;
+  s->cls = cls;
+  s->rgb = rgb;
+  s->n_points = n_points;
+  s->scan_base = scan_base;
+  for (int i = 0; i < 3; ++i) {
+    s->scale[i] = d.scale[i];
+    s->offset[i] = d.offset[i];
+    s->lo[i] = plan.lo[i];
+    s->hi[i] = plan.hi[i];
+  }
+  s->lane = lane;
+  s->layout = d.layout;
+  if (d.layout == PCQ_LAYOUT_LAS) {
+    s->record_len = d.record_len;
+    s->cls_off = (uint16_t)cls_offset_in_record(d.format);
+    s->rgb_off = (int16_t)rgb_offset_in_record(d.format);
+    s->align = field_alignment(rec, d.record_len);
+  } else {
+    s->record_len = 12;
+    s->cls_off = 0;
+    s->rgb_off = -1;
+    s->align = field_alignment(rec, 12);
+  }
+}
+
+int ensure_tile_state(pcq_ctx* ctx, uint64_t n_tiles) {
+  const uint64_t need = n_tiles + 2;
+  if (ctx->tile_state_cap < need) {
+    if (ctx->tile_state) cudaFree(ctx->tile_state);
+    ctx->tile_state = nullptr;
+    ctx->tile_state_cap = 0;
+    uint64_t cap = std::max<uint64_t>(need, 1u << 16);
+    CU(cudaMalloc(&ctx->tile_state, cap * sizeof(unsigned long long)));
+    ctx->tile_state_cap = cap;
+  }
+  CU(cudaMemsetAsync(ctx->tile_state, 0, need * sizeof(unsigned long long), ctx->stream));
+  return PCQ_OK;
+}
+
+int grow_out(pcq_collector* c, uint64_t need_records) {
+  if (c->out_cap >= need_records) return PCQ_OK;
+  uint64_t cap = std::max<uint64_t>(need_records, 4096);
+  uint8_t* nb = nullptr;
+  CU(cudaMalloc(&nb, cap * 31ull + 64));
+  if (c->d_out) {
+    if (c->out_len) CU(cudaMemcpyAsync(nb, c->d_out, c->out_len * 31ull, cudaMemcpyDeviceToDevice, c->ctx->stream));
+    CU(cudaStreamSynchronize(c->ctx->stream));
+    cudaFree(c->d_out);
+  }
+  c->d_out = nb;
+  c->out_cap = cap;
+  return PCQ_OK;
+}
+
+GridDev grid_view(const pcq_collector* c) {
+  GridDev g = c->grid;
+  g.cand_count = &c->dev->cand_count;
+  g.flags = &c->dev->flags;
+  return g;
+}
+
+int grow_cands(pcq_collector* c, uint64_t need) {
+  if (c->grid.cand_cap >= need) return PCQ_OK;
+  uint64_t cap = std::max<uint64_t>(need, 1u << 16);
+  Candidate* nb = nullptr;
+  CU(cudaMalloc(&nb, cap * sizeof(Candidate)));
+  if (c->grid.cands) {
+    if (c->cand_len)
+      CU(cudaMemcpyAsync(nb, c->grid.cands, c->cand_len * sizeof(Candidate), cudaMemcpyDeviceToDevice, c->ctx->stream));
+    CU(cudaStreamSynchronize(c->ctx->stream));
+    cudaFree(c->grid.cands);
+  }
+  c->grid.cands = nb;
+  c->grid.cand_cap = cap;
+  return PCQ_OK;
+}
+
+// drop candidates that no longer hold their cell's minimum; compacts in place through a scratch arena
+int prune_cands(pcq_collector* c) {
+  pcq_ctx* ctx = c->ctx;
+  if (c->cand_len == 0) return PCQ_OK;
+  Candidate* tmp = nullptr;
+  CU(cudaMalloc(&tmp, std::max<uint64_t>(c->cand_len, 1) * sizeof(Candidate)));
+  CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
+  GridDev g = grid_view(c);
+  if (launch_grid_prune(g, c->cand_len, tmp, &c->dev->out_count, ctx->sm_count, ctx->stream) != 0) {
+    cudaFree(tmp);
+    return fail(PCQ_ERR_CUDA, "k_grid_prune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  ctx->launches++;
+  DevBlock b;
+  int rc = read_devblock(c, &b);
+  if (rc != PCQ_OK) {
+    cudaFree(tmp);
+    return rc;
+  }
+  const uint64_t kept = b.out_count;
+  if (kept) cudaMemcpyAsync(c->grid.cands, tmp, kept * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream);
+  cudaMemcpyAsync(&c->dev->cand_count, &kept, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  c->cand_len = kept;
+  return PCQ_OK;
+}
+
+int alloc_grid_tables(pcq_collector* c, uint64_t slots, bool hashed) {
+  pcq_ctx* ctx = c->ctx;
+  unsigned long long* table = nullptr;
+  unsigned long long* hkeys = nullptr;
+  if (cudaMalloc(&table, slots * 8ull) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_NOMEM, "cannot allocate density table of %llu cells", (unsigned long long)slots);
+  }
+  if (hashed && cudaMalloc(&hkeys, slots * 8ull) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(table);
+    return fail(PCQ_ERR_NOMEM, "cannot allocate density key table of %llu slots", (unsigned long long)slots);
+  }
+  CU(cudaMemsetAsync(table, 0xFF, slots * 8ull, ctx->stream));
+  if (hkeys) CU(cudaMemsetAsync(hkeys, 0xFF, slots * 8ull, ctx->stream));
+  c->grid.table = table;
+  c->grid.hkeys = hkeys;
+  c->grid.table_slots = slots;
+  return PCQ_OK;
+}
+
+// hashed table full: quadruple it and re-insert the surviving candidates
+int rehash_grid(pcq_collector* c) {
+  pcq_ctx* ctx = c->ctx;
+  RC(prune_cands(c));
+  const uint64_t kept = c->cand_len;
+  Candidate* tmp = nullptr;
+  if (kept) {
+    CU(cudaMalloc(&tmp, kept * sizeof(Candidate)));
+    CU(cudaMemcpyAsync(tmp, c->grid.cands, kept * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(c->grid.table);
+  cudaFree(c->grid.hkeys);
+  c->grid.table = c->grid.hkeys = nullptr;
+  int rc = alloc_grid_tables(c, c->grid.table_slots * 4ull, true);
+  if (rc != PCQ_OK) {
+    cudaFree(tmp);
+    return rc;
+  }
+  const unsigned long long zero = 0;
+  cudaMemcpyAsync(&c->dev->cand_count, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemsetAsync(&c->dev->flags, 0, sizeof(uint32_t), ctx->stream);
+  c->cand_len = 0;
+  if (kept) {
+    GridDev g = grid_view(c);
+    if (launch_grid_import(g, tmp, kept, ctx->sm_count, ctx->stream) != 0) {
+      cudaFree(tmp);
+      return fail(PCQ_ERR_CUDA, "k_grid_import launch failed");
+    }
+    ctx->launches++;
+  }
+  DevBlock b;
+  rc = read_devblock(c, &b);
+  cudaFree(tmp);
+  if (rc != PCQ_OK) return rc;
+  c->cand_len = std::min<uint64_t>(b.cand_count, c->grid.cand_cap);
+  return PCQ_OK;
+}
+
+int grid_finalize(pcq_collector* c) {
+  if (c->final_valid) return PCQ_OK;
+  pcq_ctx* ctx = c->ctx;
+  const uint64_t n = c->cand_len;
+  c->final_n = 0;
+  if (n == 0) {
+    c->final_valid = true;
+    return PCQ_OK;
+  }
+  if (ctx->idx_scratch_cap < c->grid.table_slots) {
+    if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
+    ctx->idx_scratch = nullptr;
+    ctx->idx_scratch_cap = 0;
+    if (cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PCQ_ERR_NOMEM, "cannot allocate density index table");
+    }
+    ctx->idx_scratch_cap = c->grid.table_slots;
+  }
+  CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+  if (c->final_cap < n) {
+    if (c->d_final) cudaFree(c->d_final);
+    c->d_final = nullptr;
+    c->final_cap = 0;
+    CU(cudaMalloc(&c->d_final, n * 31ull + 64));
+    c->final_cap = n;
+  }
+  CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
+  GridDev g = grid_view(c);
+  if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_min_index launch failed");
+  if (launch_grid_emit(g, n, ctx->idx_scratch, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count,
+                       ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
+  ctx->launches += 2;
+  DevBlock b;
+  RC(read_devblock(c, &b));
+  c->final_n = b.out_count;
+  c->final_valid = true;
+  return PCQ_OK;
+}
+
+// one kernel launch for a prepared batch of segments; handles BUFFER / GRID capacity retries
+int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, uint64_t n_tiles, const pcq_query* q,
+              pcq_collector* const* collectors, uint32_t n_collectors, const std::vector<uint64_t>& lane_points) {
+  const int kind = collectors[0]->kind;
+  if (segs.empty() || n_tiles == 0) return PCQ_OK;
+
+  // kernel variant: staged needs one record length, 16-byte aligned ranges, and records that carry
+  // the predicate's field (LAST class queries read the class column -> direct)
+  uint32_t R = segs[0].record_len;
+  bool staged_ok = staged_supports(R);
+  bool all_last = true;
+  for (const Segment& s : segs) {
+    if (s.record_len != R) staged_ok = false;
+    if ((reinterpret_cast<uintptr_t>(s.rec) & 15u) != 0) staged_ok = false;
+    if (s.layout == PCQ_LAYOUT_LAST && q->kind == PCQ_QUERY_CLASS) staged_ok = false;
+    if (s.layout != PCQ_LAYOUT_LAST) all_last = false;
+  }
+  int variant = ctx->variant;
+  if (variant == 0) variant = staged_ok ? 2 : 1;
+  if (variant == 2 && !staged_ok) variant = 1;
+
+  std::vector<LaneDev> lanes(n_collectors);
+  const int mode = kind == PCQ_COLLECT_COUNT ? MODE_COUNT : (kind == PCQ_COLLECT_BUFFER ? MODE_SELECT : MODE_GRID);
+
+  if (kind == PCQ_COLLECT_BUFFER) {
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      if (lane_points[l] == 0) continue;
+      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 20) + lane_points[l] / 8);
+      RC(grow_out(c, c->out_len + guess));
+    }
+  } else if (kind == PCQ_COLLECT_GRID) {
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      if (lane_points[l] == 0) continue;
+      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16);
+      RC(grow_cands(c, c->cand_len + guess));
+      c->final_valid = false;
+    }
+  }
+
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      LaneDev& L = lanes[l];
+      std::memset(&L, 0, sizeof(L));
+      L.count = &c->dev->count;
+      L.out = c->d_out;
+      L.out_base = c->out_len;
+      L.out_cap = c->out_cap;
+      if (kind == PCQ_COLLECT_GRID) L.grid = grid_view(c);
+    }
+    void* d_segs = nullptr;
+    void* d_lanes = nullptr;
+    RC(upload(ctx, segs.data(), segs.size() * sizeof(Segment), &d_segs));
+    RC(upload(ctx, lanes.data(), lanes.size() * sizeof(LaneDev), &d_lanes));
+
+    ScanParams P{};
+    P.segs = static_cast<const Segment*>(d_segs);
+    P.n_segs = (uint32_t)segs.size();
+    P.query_kind = q->kind;
+    P.cls = q->cls;
+    P.n_tiles = n_tiles;
+    P.lanes = static_cast<const LaneDev*>(d_lanes);
+    if (mode == MODE_SELECT) {
+      RC(ensure_tile_state(ctx, n_tiles));
+      P.ticket = ctx->tile_state;
+      P.tile_state = ctx->tile_state + 1;
+    }
+
+    int lrc;
+    if (mode == MODE_COUNT && q->kind == PCQ_QUERY_CLASS && all_last) {
+      lrc = launch_class_count_soa(P, ctx->sm_count, ctx->stream);
+    } else {
+      lrc = launch_scan(variant, mode, P, R, ctx->sm_count, ctx->stream);
+    }
+    if (lrc != 0) return fail(PCQ_ERR_CUDA, "scan kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches++;
+
+    if (kind == PCQ_COLLECT_COUNT) return PCQ_OK;  // fully asynchronous
+
+    bool retry = false;
+    if (kind == PCQ_COLLECT_BUFFER) {
+      std::vector<DevBlock> blocks(n_collectors);
+      for (uint32_t l = 0; l < n_collectors; ++l)
+        CU(cudaMemcpyAsync(&blocks[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      for (uint32_t l = 0; l < n_collectors; ++l)
+        if (blocks[l].count > collectors[l]->out_cap) retry = true;
+      if (!retry) {
+        for (uint32_t l = 0; l < n_collectors; ++l) collectors[l]->out_len = blocks[l].count;
+        return PCQ_OK;
+      }
+      // some lane overflowed its buffer: grow to the exact size, rewind every counter, run again
+      for (uint32_t l = 0; l < n_collectors; ++l) {
+        pcq_collector* c = collectors[l];
+        RC(grow_out(c, blocks[l].count));
+        const unsigned long long len = c->out_len;
+        CU(cudaMemcpyAsync(&c->dev->count, &len, sizeof(len), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      CU(cudaStreamSynchronize(ctx->stream));
+      continue;
+    }
+
+    // GRID
+    std::vector<DevBlock> blocks(n_collectors);
+    for (uint32_t l = 0; l < n_collectors; ++l)
+      CU(cudaMemcpyAsync(&blocks[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      const DevBlock& b = blocks[l];
+      if (b.flags & kFlagAliased)
+        return fail(PCQ_ERR_ALIASED,
+                    "density grid: a matching point falls into a cell index above its bit mask; the reference's result "
+                    "for the aliased key depends on insertion order (grid_sampling.rs:62-70 vs 78-82)");
+      if (b.flags & kFlagHashFull) {
+        RC(rehash_grid(c));
+        retry = true;
+        continue;
+      }
+      if (b.flags & kFlagCandOverflow) {
+        const uint64_t attempted = b.cand_count;  // what this launch wanted in total
+        const uint64_t before = c->cand_len;
+        c->cand_len = c->grid.cand_cap;           // the arena is full of valid candidates
+        RC(prune_cands(c));
+        RC(grow_cands(c, c->cand_len + (attempted - before) + (attempted - before) / 4 + 1024));
+        CU(cudaMemsetAsync(&c->dev->flags, 0, sizeof(uint32_t), ctx->stream));
+        retry = true;
+        continue;
+      }
+      c->cand_len = b.cand_count;
+    }
+    if (!retry) return PCQ_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return fail(PCQ_ERR_NOMEM, "collector capacity did not converge");
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int pcq_ctx_create(int device, pcq_ctx** out) {
+  if (!out) return fail(PCQ_ERR_ARG, "pcq_ctx_create: null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(PCQ_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= n) return fail(PCQ_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PCQ_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  pcq_ctx* ctx = new (std::nothrow) pcq_ctx();
+  if (!ctx) return fail(PCQ_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  const char* v = std::getenv("PCQ_SCAN_VARIANT");
+  if (v) ctx->variant = std::atoi(v);
+  *out = ctx;
+  return PCQ_OK;
+}
+
+void pcq_ctx_destroy(pcq_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (UploadSlot& s : ctx->slots) {
+    if (s.host) cudaFreeHost(s.host);
+    if (s.dev) cudaFree(s.dev);
+    if (s.ev) cudaEventDestroy(s.ev);
+  }
+  if (ctx->tile_state) cudaFree(ctx->tile_state);
+  if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
+  if (ctx->part_scratch) cudaFree(ctx->part_scratch);
+  for (int i = 0; i < kChunkBuffers; ++i) {
+    if (ctx->chunk[i]) cudaFree(ctx->chunk[i]);
+    if (ctx->chunk_copied[i]) cudaEventDestroy(ctx->chunk_copied[i]);
+    if (ctx->chunk_free[i]) cudaEventDestroy(ctx->chunk_free[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int pcq_ctx_set_stream(pcq_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(PCQ_ERR_ARG, "null ctx");
+  RC(use_device(ctx));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return PCQ_OK;
+}
+
+int pcq_ctx_synchronize(pcq_ctx* ctx) {
+  if (!ctx) return fail(PCQ_ERR_ARG, "null ctx");
+  RC(use_device(ctx));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return PCQ_OK;
+}
+
+int pcq_ctx_set_scan_variant(pcq_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 2) return fail(PCQ_ERR_ARG, "bad scan variant");
+  ctx->variant = variant;
+  return PCQ_OK;
+}
+
+uint64_t pcq_ctx_launch_count(const pcq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- files ---------------------------------------------------------------------------------------
+
+int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, const char* ext, uint64_t first_point,
+                        uint64_t n_points, pcq_file** out) {
+  if (!ctx || !file_bytes || !out) return fail(PCQ_ERR_ARG, "pcq_file_stage_host: null argument");
+  const int layout = layout_of_ext(ext);
+  if (layout < 0) return fail(PCQ_ERR_FORMAT, "Unsupported file extension \"%s\" (this path serves las and last)", ext ? ext : "");
+  RC(use_device(ctx));
+  pcq_file_desc d;
+  uint8_t raw = 0;
+  RC(parse_header(file_bytes, n_bytes, layout, 1, &d, &raw));
+  if (first_point > d.n_points) return fail(PCQ_ERR_ARG, "first_point %llu beyond %llu points", (unsigned long long)first_point, (unsigned long long)d.n_points);
+  uint64_t n = std::min<uint64_t>(n_points, d.n_points - first_point);
+  const uint64_t N = d.n_points;
+  if ((uint64_t)d.point_data_off + N * (uint64_t)d.record_len > (uint64_t)n_bytes)
+    return fail(PCQ_ERR_IO, "file image holds %zu bytes but its header promises %llu points of %u bytes at offset %u",
+                n_bytes, (unsigned long long)N, d.record_len, d.point_data_off);
+  pcq_file* f = new (std::nothrow) pcq_file();
+  if (!f) return fail(PCQ_ERR_NOMEM, "out of host memory");
+  f->ctx = ctx;
+  f->desc = d;
+  f->raw_format = raw;
+  f->first_point = first_point;
+  f->n_points = n;
+  const uint8_t* src = static_cast<const uint8_t*>(file_bytes) + d.point_data_off;
+  if (layout == PCQ_LAYOUT_LAS) {
+    const size_t bytes = (size_t)n * d.record_len;
+    if (cudaMalloc(&f->owned, round_up(bytes, 256) + 256) != cudaSuccess) {
+      cudaGetLastError();
+      delete f;
+      return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM", bytes);
+    }
+    if (bytes) CU(cudaMemcpyAsync(f->owned, src + first_point * d.record_len, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    f->rec = static_cast<const uint8_t*>(f->owned);
+  } else {
+    // only the columns the path reads travel: positions, classification, colour (last.rs:80-90, 114)
+    const int rgb_k = rgb_offset_in_record(d.format);
+    const size_t pos_b = round_up((size_t)n * 12, 256);
+    const size_t cls_b = round_up((size_t)n, 256);
+    const size_t rgb_b = rgb_k >= 0 ? round_up((size_t)n * 6, 256) : 0;
+    if (cudaMalloc(&f->owned, pos_b + cls_b + rgb_b + 256) != cudaSuccess) {
+      cudaGetLastError();
+      delete f;
+      return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM", pos_b + cls_b + rgb_b);
+    }
+    uint8_t* base = static_cast<uint8_t*>(f->owned);
+    if (n) {
+      CU(cudaMemcpyAsync(base, src + first_point * 12, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(base + pos_b, src + (uint64_t)cls_offset_in_record(d.format) * N + first_point, (size_t)n,
+                         cudaMemcpyHostToDevice, ctx->stream));
+      if (rgb_k >= 0)
+        CU(cudaMemcpyAsync(base + pos_b + cls_b, src + (uint64_t)rgb_k * N + first_point * 6, (size_t)n * 6,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    }
+    f->rec = base;
+    f->cls = base + pos_b;
+    f->rgb = rgb_k >= 0 ? base + pos_b + cls_b : nullptr;
+  }
+  // the caller may reuse its buffer as soon as we return
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = f;
+  return PCQ_OK;
+}
+
+int pcq_file_wrap_device(pcq_ctx* ctx, const pcq_file_desc* desc, const void* dev_point_data, uint64_t first_point_index,
+                         pcq_file** out) {
+  if (!ctx || !desc || !out || (!dev_point_data && desc->n_points)) return fail(PCQ_ERR_ARG, "pcq_file_wrap_device: null argument");
+  if (desc->layout != PCQ_LAYOUT_LAS && desc->layout != PCQ_LAYOUT_LAST) return fail(PCQ_ERR_ARG, "bad layout");
+  if (desc->format > 10) return fail(PCQ_ERR_FORMAT, "Invalid LAS format %u", desc->format);
+  if (desc->record_len < format_record_len(desc->format))
+    return fail(PCQ_ERR_FORMAT, "point data record length %u too small for format %u", desc->record_len, desc->format);
+  pcq_file* f = new (std::nothrow) pcq_file();
+  if (!f) return fail(PCQ_ERR_NOMEM, "out of host memory");
+  f->ctx = ctx;
+  f->desc = *desc;
+  f->raw_format = desc->format;
+  f->first_point = first_point_index;
+  f->n_points = desc->n_points;
+  const uint8_t* base = static_cast<const uint8_t*>(dev_point_data);
+  const uint64_t N = desc->n_points;
+  if (desc->layout == PCQ_LAYOUT_LAS) {
+    f->rec = base;
+  } else {
+    f->rec = base;
+    f->cls = base + (uint64_t)cls_offset_in_record(desc->format) * N;
+    const int rgb_k = rgb_offset_in_record(desc->format);
+    f->rgb = rgb_k >= 0 ? base + (uint64_t)rgb_k * N : nullptr;
+  }
+  *out = f;
+  return PCQ_OK;
+}
+
+int pcq_file_set_scan_base(pcq_file* f, uint64_t scan_base) {
+  if (!f) return fail(PCQ_ERR_ARG, "null file");
+  f->has_scan_base = true;
+  f->scan_base = scan_base;
+  return PCQ_OK;
+}
+
+int pcq_file_desc_get(const pcq_file* f, pcq_file_desc* out) {
+  if (!f || !out) return fail(PCQ_ERR_ARG, "null argument");
+  *out = f->desc;
+  return PCQ_OK;
+}
+
+void pcq_file_release(pcq_file* f) {
+  if (!f) return;
+  if (f->owned) {
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->owned);
+  }
+  delete f;
+}
+
+// ---- collectors ----------------------------------------------------------------------------------
+
+int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const double gmax[3], double cell_size,
+                         pcq_collector** out) {
+  if (!ctx || !out) return fail(PCQ_ERR_ARG, "pcq_collector_create: null argument");
+  if (kind < PCQ_COLLECT_COUNT || kind > PCQ_COLLECT_GRID) return fail(PCQ_ERR_ARG, "bad collector kind %d", kind);
+  RC(use_device(ctx));
+  pcq_collector* c = new (std::nothrow) pcq_collector();
+  if (!c) return fail(PCQ_ERR_NOMEM, "out of host memory");
+  c->ctx = ctx;
+  c->kind = kind;
+  if (cudaMalloc(&c->dev, 256) != cudaSuccess) {
+    delete c;
+    return fail(PCQ_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaMemsetAsync(c->dev, 0, 256, ctx->stream);
+  if (kind == PCQ_COLLECT_GRID) {
+    if (!gmin || !gmax) {
+      pcq_collector_destroy(c);
+      return fail(PCQ_ERR_ARG, "grid collector needs bounds");
+    }
+    for (int i = 0; i < 3; ++i) {
+      if (gmin[i] > gmax[i]) {
+        pcq_collector_destroy(c);
+        return fail(PCQ_ERR_PANIC, "AABB::from_min_max: grid bounds have min > max on axis %d", i);
+      }
+      c->gmin[i] = gmin[i];
+      c->gmax[i] = gmax[i];
+    }
+    c->cell = cell_size;
+    int rc = grid_params(gmin, gmax, cell_size, c->dims, c->bits);
+    if (rc != PCQ_OK) {
+      pcq_collector_destroy(c);
+      return rc;
+    }
+    uint64_t total_bits = c->bits[0] + c->bits[1] + c->bits[2];
+    if (c->bits[0] > 62 || c->bits[1] > 62 || c->bits[2] > 62 || total_bits > 64) {
+      pcq_collector_destroy(c);
+      return fail(PCQ_ERR_GRID, "SparseGrid with %llu+%llu+%llu key bits is not representable",
+                  (unsigned long long)c->bits[0], (unsigned long long)c->bits[1], (unsigned long long)c->bits[2]);
+    }
+    GridDev& g = c->grid;
+    for (int i = 0; i < 3; ++i) {
+      g.bmin[i] = gmin[i];
+      g.bmax[i] = gmax[i];
+      g.dims_f[i] = (double)c->dims[i];  // `self.dimensions.x as f64`
+      g.mask[i] = c->bits[i] >= 64 ? ~0ull : ((1ull << c->bits[i]) - 1ull);
+    }
+    g.cell_size = cell_size;
+    g.shift_y = (uint32_t)c->bits[0];
+    g.shift_z = (uint32_t)(c->bits[0] + c->bits[1]);
+    if (g.shift_z >= 64 || g.shift_y >= 64) {
+      pcq_collector_destroy(c);
+      return fail(PCQ_ERR_GRID, "SparseGrid key shifts of 64 bits are not representable");
+    }
+    uint64_t dense_bits = 30;
+    if (const char* e = std::getenv("PCQ_DENSE_MAX_BITS")) dense_bits = (uint64_t)std::atoi(e);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    bool dense = total_bits <= dense_bits && (8ull << total_bits) <= free_b / 3;
+    uint64_t slots = dense ? (1ull << total_bits) : (1ull << 22);
+    if (const char* e = std::getenv("PCQ_HASH_SLOTS_LOG2"))
+      if (!dense) slots = 1ull << std::atoi(e);
+    rc = alloc_grid_tables(c, slots, !dense);
+    if (rc != PCQ_OK) {
+      pcq_collector_destroy(c);
+      return rc;
+    }
+  }
+  *out = c;
+  return PCQ_OK;
+}
+
+void pcq_collector_destroy(pcq_collector* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->dev) cudaFree(c->dev);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->grid.table) cudaFree(c->grid.table);
+  if (c->grid.hkeys) cudaFree(c->grid.hkeys);
+  if (c->grid.cands) cudaFree(c->grid.cands);
+  if (c->d_final) cudaFree(c->d_final);
+  if (c->d_export) cudaFree(c->d_export);
+  if (c->h_pts) cudaFreeHost(c->h_pts);
+  delete c;
+}
+
+int pcq_collector_reset(pcq_collector* c) {
+  if (!c) return fail(PCQ_ERR_ARG, "null collector");
+  pcq_ctx* ctx = c->ctx;
+  RC(use_device(ctx));
+  CU(cudaMemsetAsync(c->dev, 0, 256, ctx->stream));
+  c->scan_total = 0;
+  c->out_len = 0;
+  c->cand_len = 0;
+  c->final_valid = false;
+  c->final_n = 0;
+  if (c->kind == PCQ_COLLECT_GRID) {
+    CU(cudaMemsetAsync(c->grid.table, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+    if (c->grid.hkeys) CU(cudaMemsetAsync(c->grid.hkeys, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+  }
+  return PCQ_OK;
+}
+
+int pcq_collector_point_count(pcq_collector* c, uint64_t* out) {
+  if (!c || !out) return fail(PCQ_ERR_ARG, "null argument");
+  RC(use_device(c->ctx));
+  if (c->kind == PCQ_COLLECT_GRID) {
+    RC(grid_finalize(c));
+    *out = c->final_n;  // self.grid.points().count(), collect_points.rs:124-126
+    return PCQ_OK;
+  }
+  DevBlock b;
+  RC(read_devblock(c, &b));
+  *out = b.count;
+  return PCQ_OK;
+}
+
+int pcq_collector_points_device(pcq_collector* c, const void** out_dev_points, uint64_t* out_n) {
+  if (!c || !out_dev_points || !out_n) return fail(PCQ_ERR_ARG, "null argument");
+  RC(use_device(c->ctx));
+  *out_dev_points = nullptr;
+  *out_n = 0;
+  if (c->kind == PCQ_COLLECT_COUNT) return PCQ_OK;  // points() == None
+  if (c->kind == PCQ_COLLECT_BUFFER) {
+    CU(cudaStreamSynchronize(c->ctx->stream));
+    *out_dev_points = c->d_out;
+    *out_n = c->out_len;
+    return PCQ_OK;
+  }
+  RC(grid_finalize(c));
+  *out_dev_points = c->d_final;
+  *out_n = c->final_n;
+  return PCQ_OK;
+}
+
+int pcq_collector_points(pcq_collector* c, const pcq_point** out_points, uint64_t* out_n) {
+  if (!c || !out_points || !out_n) return fail(PCQ_ERR_ARG, "null argument");
+  const void* dptr = nullptr;
+  uint64_t n = 0;
+  RC(pcq_collector_points_device(c, &dptr, &n));
+  *out_points = nullptr;
+  *out_n = 0;
+  if (n == 0) return PCQ_OK;
+  if (c->h_cap < n) {
+    if (c->h_pts) cudaFreeHost(c->h_pts);
+    c->h_pts = nullptr;
+    c->h_cap = 0;
+    uint64_t cap = std::max<uint64_t>(n, 4096);
+    if (cudaMallocHost(&c->h_pts, cap * 31ull) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PCQ_ERR_NOMEM, "cannot pin %llu bytes of host memory", (unsigned long long)(cap * 31ull));
+    }
+    c->h_cap = cap;
+  }
+  CU(cudaMemcpyAsync(c->h_pts, dptr, n * 31ull, cudaMemcpyDeviceToHost, c->ctx->stream));
+  CU(cudaStreamSynchronize(c->ctx->stream));
+  *out_points = static_cast<const pcq_point*>(c->h_pts);
+  *out_n = n;
+  return PCQ_OK;
+}
+
+// ---- the scan ------------------------------------------------------------------------------------
+
+static int check_search_args(pcq_ctx* ctx, uint32_t n_files, const pcq_query* q, pcq_collector* const* collectors,
+                             uint32_t n_collectors) {
+  if (!ctx || !q || !collectors) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
+  if (n_collectors != 1 && n_collectors != n_files)
+    return fail(PCQ_ERR_ARG, "n_collectors must be 1 (sequential) or n_files (parallel), got %u for %u files", n_collectors, n_files);
+  for (uint32_t l = 0; l < n_collectors; ++l) {
+    if (!collectors[l]) return fail(PCQ_ERR_ARG, "null collector %u", l);
+    if (collectors[l]->kind != collectors[0]->kind) return fail(PCQ_ERR_ARG, "collectors of one search must be of one kind");
+    if (collectors[l]->ctx != ctx) return fail(PCQ_ERR_ARG, "collector %u belongs to another context", l);
+  }
+  if (q->kind == PCQ_QUERY_BOUNDS)
+    for (int i = 0; i < 3; ++i)
+      if (q->qmin[i] > q->qmax[i]) return fail(PCQ_ERR_PANIC, "AABB::from_min_max: query bounds have min > max on axis %d", i);
+  return PCQ_OK;
+}
+
+int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, const pcq_query* query,
+                     pcq_collector* const* collectors, uint32_t n_collectors) {
+  RC(check_search_args(ctx, n_files, query, collectors, n_collectors));
+  if (n_files == 0) return PCQ_OK;
+  if (!files) return fail(PCQ_ERR_ARG, "null files");
+  RC(use_device(ctx));
+
+  std::vector<Segment> segs;
+  segs.reserve(n_files);
+  std::vector<uint64_t> lane_points(n_collectors, 0);
+  std::vector<uint64_t> lane_first(n_collectors, ~0ull);
+  uint64_t tile_cursor = 0;
+  for (uint32_t i = 0; i < n_files; ++i) {
+    pcq_file* f = files[i];
+    if (!f) return fail(PCQ_ERR_ARG, "null file %u", i);
+    if (f->ctx != ctx) return fail(PCQ_ERR_ARG, "file %u belongs to another context", i);
+    const uint32_t lane = n_collectors == 1 ? 0 : i;
+    pcq_collector* c = collectors[lane];
+    const uint64_t base = f->has_scan_base ? f->scan_base : c->scan_total;
+    if (!f->has_scan_base) c->scan_total += f->n_points;
+    SegmentPlan plan;
+    RC(plan_file(f->desc, f->raw_format, query, &plan));
+    if (plan.skip || f->n_points == 0) continue;
+    Segment s;
+    fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base);
+    s.first_tile = tile_cursor;
+    if (lane_first[lane] == ~0ull) lane_first[lane] = tile_cursor;
+    s.lane_first_tile = lane_first[lane];
+    tile_cursor += (f->n_points + kTilePts - 1) / kTilePts;
+    lane_points[lane] += f->n_points;
+    segs.push_back(s);
+  }
+  return run_batch(ctx, segs, tile_cursor, query, collectors, n_collectors, lane_points);
+}
+
+int pcq_host_alloc(size_t n_bytes, void** out) {
+  if (!out) return fail(PCQ_ERR_ARG, "null out");
+  if (cudaMallocHost(out, n_bytes ? n_bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes of host memory", n_bytes);
+  }
+  return PCQ_OK;
+}
+
+void pcq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// Host-staged scan: file images stream through a ring of HBM chunk buffers; the copy of chunk k+1
+// overlaps the scan of chunk k.  Replaces mmap + page-fault driven reads (las.rs:24-31).
+int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
+                          uint32_t n_files, const pcq_query* query, pcq_collector* const* collectors,
+                          uint32_t n_collectors) {
+  RC(check_search_args(ctx, n_files, query, collectors, n_collectors));
+  if (n_files == 0) return PCQ_OK;
+  if (!file_bytes || !n_bytes || !exts) return fail(PCQ_ERR_ARG, "null argument");
+  RC(use_device(ctx));
+  const int kind = collectors[0]->kind;
+
+  size_t chunk_bytes = 64u << 20;
+  if (const char* e = std::getenv("PCQ_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
+  if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (ctx->chunk_cap < chunk_bytes) {
+    for (int b = 0; b < kChunkBuffers; ++b) {
+      if (ctx->chunk[b]) cudaFree(ctx->chunk[b]);
+      ctx->chunk[b] = nullptr;
+    }
+    for (int b = 0; b < kChunkBuffers; ++b) CU(cudaMalloc(&ctx->chunk[b], chunk_bytes + 1024));
+    ctx->chunk_cap = chunk_bytes;
+  }
+  for (int b = 0; b < kChunkBuffers; ++b) {
+    if (!ctx->chunk_copied[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_copied[b], cudaEventDisableTiming));
+    if (!ctx->chunk_free[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_free[b], cudaEventDisableTiming));
+  }
+
+  // plan: one entry per (file, point range)
+  struct Piece {
+    uint32_t file;
+    uint64_t first, n;
+  };
+  struct FilePlan {
+    pcq_file_desc d;
+    uint8_t raw;
+    SegmentPlan plan;
+    uint64_t base;
+    uint32_t lane;
+    bool need_pos, need_cls, need_rgb;
+  };
+  std::vector<FilePlan> fps(n_files);
+  std::vector<Piece> pieces;
+  for (uint32_t i = 0; i < n_files; ++i) {
+    FilePlan& fp = fps[i];
+    const int layout = layout_of_ext(exts[i]);
+    if (layout < 0) return fail(PCQ_ERR_FORMAT, "Unsupported file extension \"%s\"", exts[i] ? exts[i] : "");
+    RC(parse_header(file_bytes[i], n_bytes[i], layout, 1, &fp.d, &fp.raw));
+    if ((uint64_t)fp.d.point_data_off + fp.d.n_points * (uint64_t)fp.d.record_len > (uint64_t)n_bytes[i])
+      return fail(PCQ_ERR_IO, "file image %u is shorter than its header promises", i);
+    fp.lane = n_collectors == 1 ? 0 : i;
+    pcq_collector* c = collectors[fp.lane];
+    fp.base = c->scan_total;
+    c->scan_total += fp.d.n_points;
+    RC(plan_file(fp.d, fp.raw, query, &fp.plan));
+    if (fp.plan.skip || fp.d.n_points == 0) continue;
+    const bool emit = kind != PCQ_COLLECT_COUNT;
+    fp.need_pos = query->kind == PCQ_QUERY_BOUNDS || emit;
+    fp.need_cls = query->kind == PCQ_QUERY_CLASS || emit;
+    fp.need_rgb = emit && rgb_offset_in_record(fp.d.format) >= 0;
+    uint64_t per_point = layout == PCQ_LAYOUT_LAS
+                             ? fp.d.record_len
+                             : (fp.need_pos ? 12 : 0) + (fp.need_cls ? 1 : 0) + (fp.need_rgb ? 6 : 0);
+    uint64_t pts = (chunk_bytes - 1024) / per_point;
+    pts = std::max<uint64_t>(kTilePts, pts / kTilePts * kTilePts);
+    for (uint64_t first = 0; first < fp.d.n_points; first += pts)
+      pieces.push_back({i, first, std::min<uint64_t>(pts, fp.d.n_points - first)});
+  }
+
+  struct Staged {
+    const uint8_t *rec, *cls, *rgb;
+  };
+  std::vector<Staged> staged(pieces.size());
+  auto issue_copy = [&](size_t j) -> int {
+    const Piece& pc = pieces[j];
+    const FilePlan& fp = fps[pc.file];
+    const int b = (int)(j % kChunkBuffers);
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_free[b], 0));
+    uint8_t* dst = static_cast<uint8_t*>(ctx->chunk[b]);
+    const uint8_t* src = static_cast<const uint8_t*>(file_bytes[pc.file]) + fp.d.point_data_off;
+    const uint64_t N = fp.d.n_points;
+    Staged st{nullptr, nullptr, nullptr};
+    if (fp.d.layout == PCQ_LAYOUT_LAS) {
+      CU(cudaMemcpyAsync(dst, src + pc.first * fp.d.record_len, pc.n * fp.d.record_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+      st.rec = dst;
+    } else {
+      size_t o = 0;
+      if (fp.need_pos) {
+        CU(cudaMemcpyAsync(dst + o, src + pc.first * 12, pc.n * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+        st.rec = dst + o;
+        o += round_up(pc.n * 12, 256);
+      } else {
+        st.rec = dst;  // never dereferenced by a class count
+      }
+      if (fp.need_cls) {
+        CU(cudaMemcpyAsync(dst + o, src + (uint64_t)cls_offset_in_record(fp.d.format) * N + pc.first, pc.n,
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        st.cls = dst + o;
+        o += round_up(pc.n, 256);
+      }
+      if (fp.need_rgb) {
+        CU(cudaMemcpyAsync(dst + o, src + (uint64_t)rgb_offset_in_record(fp.d.format) * N + pc.first * 6, pc.n * 6,
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        st.rgb = dst + o;
+      }
+    }
+    staged[j] = st;
+    CU(cudaEventRecord(ctx->chunk_copied[b], ctx->copy_stream));
+    return PCQ_OK;
+  };
+
+  // buffers start out free
+  for (int b = 0; b < kChunkBuffers; ++b) CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
+  const size_t prefetch = kChunkBuffers - 1;
+  for (size_t j = 0; j < std::min(prefetch, pieces.size()); ++j) RC(issue_copy(j));
+  for (size_t j = 0; j < pieces.size(); ++j) {
+    if (j + prefetch < pieces.size()) RC(issue_copy(j + prefetch));
+    const Piece& pc = pieces[j];
+    const FilePlan& fp = fps[pc.file];
+    const int b = (int)(j % kChunkBuffers);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->chunk_copied[b], 0));
+    std::vector<Segment> segs(1);
+    fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan, fp.lane, fp.base + pc.first);
+    segs[0].first_tile = 0;
+    segs[0].lane_first_tile = 0;
+    std::vector<uint64_t> lane_points(n_collectors, 0);
+    lane_points[fp.lane] = pc.n;
+    // run_batch indexes lanes by Segment::lane, so hand it the full collector array
+    RC(run_batch(ctx, segs, (pc.n + kTilePts - 1) / kTilePts, query, collectors, n_collectors, lane_points));
+    CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
+  }
+  return PCQ_OK;
+}
+
+// ---- multi-GPU density exchange --------------------------------------------------------------------
+
+int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** out_dev_candidates, uint64_t* counts) {
+  if (!c || !out_dev_candidates || !counts || n_parts == 0) return fail(PCQ_ERR_ARG, "null argument");
+  if (c->kind != PCQ_COLLECT_GRID) return fail(PCQ_ERR_ARG, "not a grid collector");
+  pcq_ctx* ctx = c->ctx;
+  RC(use_device(ctx));
+  *out_dev_candidates = nullptr;
+  for (uint32_t p = 0; p < n_parts; ++p) counts[p] = 0;
+  const uint64_t n = c->cand_len;
+  if (n == 0) return PCQ_OK;
+  if (ctx->idx_scratch_cap < c->grid.table_slots) {
+    if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
+    ctx->idx_scratch = nullptr;
+    ctx->idx_scratch_cap = 0;
+    CU(cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull));
+    ctx->idx_scratch_cap = c->grid.table_slots;
+  }
+  if (ctx->part_scratch_cap < n_parts) {
+    if (ctx->part_scratch) cudaFree(ctx->part_scratch);
+    ctx->part_scratch = nullptr;
+    CU(cudaMalloc(&ctx->part_scratch, 2ull * n_parts * sizeof(unsigned long long)));
+    ctx->part_scratch_cap = n_parts;
+  }
+  CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+  CU(cudaMemsetAsync(ctx->part_scratch, 0, 2ull * n_parts * sizeof(unsigned long long), ctx->stream));
+  GridDev g = grid_view(c);
+  if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");
+  if (launch_grid_emit(g, n, ctx->idx_scratch, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr,
+                       ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "launch failed");
+  ctx->launches += 2;
+  std::vector<unsigned long long> h(n_parts);
+  CU(cudaMemcpyAsync(h.data(), ctx->part_scratch, n_parts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> cursor(n_parts);
+  uint64_t total = 0;
+  for (uint32_t p = 0; p < n_parts; ++p) {
+    cursor[p] = total;
+    counts[p] = h[p];
+    total += h[p];
+  }
+  if (c->export_cap < total) {
+    if (c->d_export) cudaFree(c->d_export);
+    c->d_export = nullptr;
+    c->export_cap = 0;
+    CU(cudaMalloc(&c->d_export, std::max<uint64_t>(total, 1) * sizeof(Candidate)));
+    c->export_cap = total;
+  }
+  CU(cudaMemcpyAsync(ctx->part_scratch + n_parts, cursor.data(), n_parts * sizeof(unsigned long long),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  if (launch_grid_emit(g, n, ctx->idx_scratch, 1, n_parts, ctx->part_scratch, ctx->part_scratch + n_parts, c->d_export,
+                       nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "launch failed");
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out_dev_candidates = c->d_export;
+  return PCQ_OK;
+}
+
+int pcq_grid_import_candidates(pcq_collector* c, const void* dev_candidates, uint64_t n) {
+  if (!c) return fail(PCQ_ERR_ARG, "null collector");
+  if (c->kind != PCQ_COLLECT_GRID) return fail(PCQ_ERR_ARG, "not a grid collector");
+  if (n == 0) return PCQ_OK;
+  if (!dev_candidates) return fail(PCQ_ERR_ARG, "null candidates");
+  pcq_ctx* ctx = c->ctx;
+  RC(use_device(ctx));
+  c->final_valid = false;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    RC(grow_cands(c, c->cand_len + n));
+    GridDev g = grid_view(c);
+    if (launch_grid_import(g, static_cast<const Candidate*>(dev_candidates), n, ctx->sm_count, ctx->stream) != 0)
+      return fail(PCQ_ERR_CUDA, "k_grid_import launch failed");
+    ctx->launches++;
+    DevBlock b;
+    RC(read_devblock(c, &b));
+    if (b.flags & kFlagHashFull) {
+      RC(rehash_grid(c));
+      continue;
+    }
+    c->cand_len = std::min<uint64_t>(b.cand_count, c->grid.cand_cap);
+    return PCQ_OK;
+  }
+  return fail(PCQ_ERR_NOMEM, "density table did not converge");
+}
+
+}  // extern "C"

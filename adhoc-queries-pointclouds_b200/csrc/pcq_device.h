@@ -1,0 +1,109 @@
+// pcq_device.h — structures shared between the host side of libpcq and its CUDA kernels.
+//
+// Vocabulary: a *segment* is one point range of one file as the scan kernels see it; a *tile* is
+// kTilePts consecutive records of one segment (the unit of scheduling, staging and of the
+// decoupled look-back); a *lane* is one ResultCollector (collect_points.rs) — one lane for
+// run_search_sequential, one lane per file for run_search_parallel (main.rs:122-183).
+#pragma once
+#include <cstdint>
+
+#include "../../include/pcq.h"
+
+namespace pcq {
+
+constexpr int kTilePts = 512;  // records per tile
+constexpr int kBlock = 256;    // threads per CTA of the scan kernels
+constexpr int kPPT = kTilePts / kBlock;
+
+enum Mode : int { MODE_COUNT = 0, MODE_SELECT = 1, MODE_GRID = 2 };
+
+// One point range of one file, as resident in HBM.
+struct alignas(16) Segment {
+  const uint8_t* rec;   // LAS: record 0 of the range.  LAST: positions column (12-byte stride)
+  const uint8_t* cls;   // LAST: classification column of the range (LAS: unused)
+  const uint8_t* rgb;   // LAST: colour column of the range, or nullptr (LAS: unused)
+  uint64_t n_points;
+  uint64_t first_tile;  // index of this segment's first tile within the launch
+  uint64_t lane_first_tile;  // first tile of this segment's lane within the launch (look-back stops here)
+  uint64_t scan_base;   // collector-wide scan index of point 0 of the range
+  double scale[3];      // raw_header.{x,y,z}_scale_factor
+  double offset[3];     // raw_header.{x,y,z}_offset
+  int32_t lo[3];        // query_bounds_local.min(), clamped into i32 (las.rs:88-99)
+  int32_t hi[3];        // query_bounds_local.max(), clamped into i32
+  uint32_t record_len;  // LAS: point_data_record_length.  LAST: 12
+  uint32_t lane;
+  uint16_t cls_off;     // LAS: offset of the classification byte inside a record (15 / 16)
+  int16_t rgb_off;      // LAS: offset of the colour inside a record, -1 if the format has none
+  uint8_t layout;       // pcq_layout
+  uint8_t align;        // 4, 2 or 1: alignment every x/y/z field of the range is guaranteed to have
+  uint8_t pad_[2];
+};
+
+// 64-byte density candidate == pcq_cell_candidate of the C ABI.
+struct alignas(16) Candidate {
+  uint64_t key;
+  uint64_t dist_bits;
+  uint64_t scan_idx;
+  uint8_t point[31];
+  uint8_t pad_[9];
+};
+static_assert(sizeof(Candidate) == 64, "candidate must be 64 bytes");
+static_assert(sizeof(pcq_cell_candidate) == 64, "ABI candidate must be 64 bytes");
+
+// SparseGrid (grid_sampling.rs:9-15) as the insert kernel sees it.
+struct GridDev {
+  double bmin[3];
+  double bmax[3];
+  double dims_f[3];     // self.dimensions.{x,y,z} as f64
+  double cell_size;
+  uint64_t mask[3];     // (1 << bits) - 1
+  uint32_t shift_y;     // bits.x
+  uint32_t shift_z;     // bits.x + bits.y
+  unsigned long long* table;  // per cell: f64 bits of the smallest squared distance seen (init ~0)
+  uint64_t table_slots;       // dense: 1 << (bits.x + bits.y + bits.z).  hashed: power of two
+  unsigned long long* hkeys;  // hashed only: cell key per slot (init ~0), nullptr when dense
+  Candidate* cands;
+  unsigned long long* cand_count;
+  uint64_t cand_cap;
+  uint32_t* flags;      // bit 0: aliased key seen, bit 1: candidate arena overflow, bit 2: hash full
+};
+
+constexpr uint32_t kFlagAliased = 1u;
+constexpr uint32_t kFlagCandOverflow = 2u;
+constexpr uint32_t kFlagHashFull = 4u;
+
+// Per-lane (per-collector) device state for one launch.
+struct LaneDev {
+  unsigned long long* count;  // matches (COUNT / BUFFER collectors)
+  uint8_t* out;               // BUFFER: 31-byte records
+  uint64_t out_base;          // BUFFER: records already in `out` before this launch
+  uint64_t out_cap;           // BUFFER: capacity of `out` in records
+  GridDev grid;               // GRID
+};
+
+struct ScanParams {
+  const Segment* segs;
+  uint32_t n_segs;
+  uint32_t query_kind;  // pcq_query_kind
+  uint32_t cls;         // class byte of a class query
+  uint32_t pad_;
+  uint64_t n_tiles;
+  const LaneDev* lanes;
+  unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
+  unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
+};
+
+// launch wrappers implemented in kernels.cu (stream is a cudaStream_t); 0 = ok, < 0 = CUDA error
+bool staged_supports(uint32_t record_len);
+int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int sm_count, void* stream);
+int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
+int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count, int sm_count,
+                      void* stream);
+int launch_grid_min_index(const GridDev& g, uint64_t n, unsigned long long* idx_table, int sm_count, void* stream);
+// mode 0: count winners per owner part, 1: write winners as candidates into their parts, 2: write 31-byte points
+int launch_grid_emit(const GridDev& g, uint64_t n, unsigned long long* idx_table, int mode, uint32_t n_parts,
+                     unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
+                     uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream);
+int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream);
+
+}  // namespace pcq

@@ -1,0 +1,221 @@
+/*
+ * pcq.h — C ABI of the B200-native full-scan point-cloud query path.
+ *
+ * This is the drop-in boundary for ONE path of igd-geo/adhoc-queries-pointclouds: the `--optimized`
+ * full scan of uncompressed LAS (row-major records) and LAST (columnar) files that evaluates
+ * bounding-box / class / max-density predicates on every point.  The reference has no FFI; the seam
+ * this library sits behind is the Rust trait pair
+ *
+ *     Searcher::search_file(&self, path, &SearchImplementation, &mut dyn ResultCollector)
+ *                                                           query/src/search/searcher.rs:24-31
+ *     ResultCollector::{collect_one, points, points_ref, point_count}
+ *                                                           query/src/collect_points.rs:7-12
+ *
+ * and the four free functions it dispatches to for SearchImplementation::Optimized
+ * (query/src/search/las.rs:52, 192; query/src/search/last.rs:46, 213).  A per-point `collect_one`
+ * callback cannot cross a device boundary, so the three collector kinds of collect_points.rs are
+ * exported as device-resident objects that are filled in bulk; a Rust `impl Searcher` shim binds
+ * these entry points 1:1.
+ *
+ * Conventions: plain pointers and sizes only; every function returns PCQ_OK (0) or a negative
+ * pcq_status and records a thread-local message readable through pcq_last_error(); nothing throws or
+ * aborts across the boundary; the caller owns every input buffer, the library owns device memory and
+ * every array it hands back until the owning object is destroyed.  There is NO CPU fallback: every
+ * entry point that scans points runs hand-written sm_100a CUDA kernels and fails with PCQ_ERR_CUDA
+ * when no usable GPU is present.
+ */
+#ifndef PCQ_H
+#define PCQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Status codes.  PCQ_ERR_FORMAT  ~ an `Err(anyhow!(..))` of the reference (bad header / bad format),
+ *                PCQ_ERR_PANIC   ~ a place where the reference panics (AABB::from_min_max with
+ *                                  min > max: las.rs:61, 88; last.rs:55, 98; main.rs:80),
+ *                PCQ_ERR_GRID    ~ SparseGrid::new's "Too many cells" error (grid_sampling.rs:32-34),
+ *                PCQ_ERR_ALIASED ~ density insert hit the key-aliasing case whose result depends on
+ *                                  insertion order (grid_sampling.rs:62-70 vs 78-82) and the
+ *                                  collector was created without replay support.
+ * ---------------------------------------------------------------------------------------------- */
+enum pcq_status {
+  PCQ_OK = 0,
+  PCQ_ERR_ARG = -1,
+  PCQ_ERR_FORMAT = -2,
+  PCQ_ERR_PANIC = -3,
+  PCQ_ERR_CUDA = -4,
+  PCQ_ERR_NOMEM = -5,
+  PCQ_ERR_GRID = -6,
+  PCQ_ERR_ALIASED = -7,
+  PCQ_ERR_IO = -8
+};
+
+/* readers::Point (readers/src/lib.rs:10-19): #[repr(C, packed)], 31 bytes,
+ * position f64x3 @0, color u16x3 @24, classification u8 @30. */
+typedef struct __attribute__((packed)) pcq_point {
+  double pos[3];
+  uint16_t rgb[3];
+  uint8_t cls;
+} pcq_point;
+
+enum pcq_layout { PCQ_LAYOUT_LAS = 0, PCQ_LAYOUT_LAST = 1 };
+
+/* What the scan needs from las::raw::Header / las::Header (las.rs:59-60, 73-78, 101-103;
+ * last.rs:53-54, 80-90, 220-225): LAS 1.x public header block fields. */
+typedef struct pcq_file_desc {
+  uint8_t layout;          /* pcq_layout */
+  uint8_t format;          /* point_data_record_format after optional `&= 0b1111` (last.rs:222) */
+  uint16_t record_len;     /* point_data_record_length */
+  uint32_t point_data_off; /* offset_to_point_data */
+  uint64_t n_points;       /* header.number_of_points() */
+  double scale[3];
+  double offset[3];
+  double hdr_min[3];       /* header.bounds().min */
+  double hdr_max[3];       /* header.bounds().max */
+} pcq_file_desc;
+
+/* BoundsSearcher / ClassSearcher (searcher.rs:33-91, 94-152). */
+enum pcq_query_kind { PCQ_QUERY_BOUNDS = 0, PCQ_QUERY_CLASS = 1 };
+typedef struct pcq_query {
+  uint8_t kind;   /* pcq_query_kind */
+  uint8_t cls;    /* ClassSearcher::class; whole-byte compare (las.rs:229, last.rs:260) */
+  uint8_t pad_[6];
+  double qmin[3]; /* BoundsSearcher::bounds.min() */
+  double qmax[3]; /* BoundsSearcher::bounds.max() */
+} pcq_query;
+
+/* CountCollector / BufferCollector / GridSampledCollector (collect_points.rs:72-98, 14-44, 100-127). */
+enum pcq_collector_kind { PCQ_COLLECT_COUNT = 0, PCQ_COLLECT_BUFFER = 1, PCQ_COLLECT_GRID = 2 };
+
+typedef struct pcq_ctx pcq_ctx;             /* one GPU + stream + scratch arenas (one per process/rank) */
+typedef struct pcq_file pcq_file;           /* a file (or a point range of one) resident in HBM       */
+typedef struct pcq_collector pcq_collector; /* device-resident ResultCollector                        */
+
+/* ---- library --------------------------------------------------------------------------------- */
+const char* pcq_last_error(void);
+const char* pcq_version(void);
+
+/* ---- host-side logic of the path (no GPU needed) ----------------------------------------------- */
+
+/* parse_las_header + Header::from_raw (las.rs:33-36, 59-60; last.rs:36-39, 53-54, 220-223).
+ * `mask_format` != 0 applies `point_data_record_format &= 0b1111` first, as the LAST class search and
+ * LASTReader do (last.rs:222, last_reader.rs:76-79); the two bounds searches do not (last.rs:53-54). */
+int pcq_parse_header(const void* bytes, size_t n_bytes, int layout, int mask_format, pcq_file_desc* out);
+
+/* Query bounds -> integer coordinates in the local space of the file (las.rs:88-99, last.rs:98-109),
+ * including the reference's use of x_scale_factor for min.y / min.z.  PCQ_ERR_PANIC when any
+ * lo > hi (AABB::<i64>::from_min_max panics). */
+int pcq_local_bounds(const pcq_file_desc* desc, const double qmin[3], const double qmax[3],
+                     int64_t lo[3], int64_t hi[3]);
+
+/* file_bounds.intersects(bounds) (las.rs:82, last.rs:92): closed-interval overlap on all axes.
+ * Writes 0/1 to *out.  PCQ_ERR_PANIC when the header bounds have min > max (las.rs:61). */
+int pcq_file_intersects(const pcq_file_desc* desc, const double qmin[3], const double qmax[3], int* out);
+
+/* SparseGrid::new (grid_sampling.rs:18-47): cells per dimension and bits per dimension. */
+int pcq_grid_params(const double gmin[3], const double gmax[3], double cell_size,
+                    uint64_t dims[3], uint64_t bits[3]);
+
+/* ---- device context ---------------------------------------------------------------------------- */
+int pcq_ctx_create(int device, pcq_ctx** out);
+void pcq_ctx_destroy(pcq_ctx* ctx);
+/* Use a caller-owned stream (a cudaStream_t passed as void*) for all work of this context. */
+int pcq_ctx_set_stream(pcq_ctx* ctx, void* cuda_stream);
+int pcq_ctx_synchronize(pcq_ctx* ctx);
+/* Scan kernel variant: 0 = auto, 1 = direct (vectorised global loads), 2 = staged (bulk-async tiles
+ * into shared memory behind an mbarrier pipeline).  For measurement; results are identical. */
+int pcq_ctx_set_scan_variant(pcq_ctx* ctx, int variant);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t pcq_ctx_launch_count(const pcq_ctx* ctx);
+
+/* ---- files in HBM ------------------------------------------------------------------------------ */
+
+/* Replaces open_file_reader's mmap (las.rs:24-31): copies the point range
+ * [first_point, first_point + n_points) of a whole LAS/LAST file image from host memory to HBM
+ * (256-byte aligned; for LAST only the position / classification / colour columns travel).
+ * n_points == UINT64_MAX means "to the end of the file".  `ext` is "las" or "last". */
+int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, const char* ext,
+                        uint64_t first_point, uint64_t n_points, pcq_file** out);
+
+/* Wraps point data that is already resident in HBM.  For LAS `dev_point_data` points at record 0;
+ * for LAST it points at the start of the transposed record block (column of the field at record
+ * offset k starts at dev_point_data + k * desc->n_points, last_reader.rs:88-144).  The memory stays
+ * owned by the caller.  `first_point_index` is the scan index of record 0 inside its file. */
+int pcq_file_wrap_device(pcq_ctx* ctx, const pcq_file_desc* desc, const void* dev_point_data,
+                         uint64_t first_point_index, pcq_file** out);
+
+/* Scan index of this range's record 0 within its collector (ties in the density fold keep the point
+ * with the smaller scan index, i.e. the one the sequential reference loop meets first).  Default:
+ * the number of points of all files fed to the collector before this one.  Set it explicitly when
+ * files or point ranges of one logical scan are sharded over several GPUs. */
+int pcq_file_set_scan_base(pcq_file* f, uint64_t scan_base);
+
+int pcq_file_desc_get(const pcq_file* f, pcq_file_desc* out);
+void pcq_file_release(pcq_file* f);
+
+/* ---- collectors -------------------------------------------------------------------------------- */
+
+/* kind = PCQ_COLLECT_GRID uses gmin/gmax/cell_size exactly as GridSampledCollector::new(bounds,
+ * cell_size) (collect_points.rs:104-108; main.rs:253-264); other kinds ignore them (may be NULL). */
+int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const double gmax[3],
+                         double cell_size, pcq_collector** out);
+void pcq_collector_destroy(pcq_collector* c);
+/* Forget everything collected so far (keeps allocations). */
+int pcq_collector_reset(pcq_collector* c);
+/* ResultCollector::point_count (collect_points.rs:11). */
+int pcq_collector_point_count(pcq_collector* c, uint64_t* out);
+/* ResultCollector::points / points_ref (collect_points.rs:9-10): host array owned by the collector,
+ * valid until the next call on it.  BUFFER: scan order.  GRID: arbitrary order (HashMap::values).
+ * COUNT: *out_points = NULL, *out_n = 0 and the call returns PCQ_OK (`None`). */
+int pcq_collector_points(pcq_collector* c, const pcq_point** out_points, uint64_t* out_n);
+/* Same records, left in HBM (device pointer, 31-byte stride). */
+int pcq_collector_points_device(pcq_collector* c, const void** out_dev_points, uint64_t* out_n);
+
+/* ---- the scan ---------------------------------------------------------------------------------- */
+
+/* Searcher::search_file over a batch of resident files with SearchImplementation::Optimized.
+ * n_collectors == 1: every file feeds collectors[0] in `files` order (run_search_sequential,
+ * main.rs:122-144).  n_collectors == n_files: file i feeds collectors[i] (run_search_parallel,
+ * main.rs:146-183).  All collectors of one call must be of one kind.  Asynchronous on the
+ * context's stream; collector getters synchronise. */
+int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, const pcq_query* query,
+                     pcq_collector* const* collectors, uint32_t n_collectors);
+
+/* Host-staged variant: whole file images in (ideally pinned) host memory are streamed through a ring
+ * of HBM chunk buffers, copies overlapped with the scan; nothing stays resident. */
+int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
+                          const char* const* exts, uint32_t n_files, const pcq_query* query,
+                          pcq_collector* const* collectors, uint32_t n_collectors);
+
+/* Pinned host memory helpers for callers that want full-speed staging. */
+int pcq_host_alloc(size_t n_bytes, void** out);
+void pcq_host_free(void* p);
+
+/* ---- multi-GPU density exchange (one process per GPU; the caller moves the bytes, e.g. with an
+ *      NCCL all-to-all) ------------------------------------------------------------------------- */
+
+/* One 64-byte candidate per locally occupied cell. */
+typedef struct pcq_cell_candidate {
+  uint64_t key;       /* SparseGrid cell key (grid_sampling.rs:68-70) */
+  uint64_t dist_bits; /* f64 bits of the squared distance to the cell centre */
+  uint64_t scan_idx;  /* global scan index: ties keep the first point, as the strict `<` does */
+  pcq_point point;    /* 31 bytes */
+  uint8_t pad_[9];
+} pcq_cell_candidate;
+
+/* Emits the local winners of a GRID collector partitioned by owner = mix64(key) % n_parts into one
+ * device array; counts[p] candidates for part p, parts stored back to back. */
+int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** out_dev_candidates,
+                               uint64_t* counts /* n_parts */);
+/* Folds candidates received from peers (device pointer) into this collector's grid. */
+int pcq_grid_import_candidates(pcq_collector* c, const void* dev_candidates, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCQ_H */
