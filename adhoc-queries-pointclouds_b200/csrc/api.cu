@@ -56,6 +56,9 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 struct pcq_ctx {
+  // files and collectors keep their context alive: pcq_ctx_destroy only marks it closing while any exist
+  int refs = 0;
+  bool closing = false;
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
@@ -217,7 +220,7 @@ int plan_file(const pcq_file_desc& d, uint8_t raw_format, const pcq_query* q, Se
 }
 
 void fill_segment(Segment* s, const pcq_file_desc& d, const uint8_t* rec, const uint8_t* cls, const uint8_t* rgb,
-                  uint64_t n_points, const SegmentPlan& plan, uint32_t lane, uint64_t scan_base) {
+                  uint64_t n_points, const SegmentPlan& plan, uint32_t lane, uint64_t scan_base, uint32_t query_kind) {
   std::memset(s, 0, sizeof(*s));
   s->rec = rec;
   s->cls = cls;
@@ -234,7 +237,9 @@ void fill_segment(Segment* s, const pcq_file_desc& d, const uint8_t* rec, const 
   s->layout = d.layout;
   if (d.layout == PCQ_LAYOUT_LAS) {
     s->record_len = d.record_len;
-    s->cls_off = (uint16_t)cls_offset_in_record(d.format);
+    // the LAS bounds search skips 3 bytes after z and reads "the" classification at +15 whatever the
+    // format (las.rs:80, 121-124); the LAS class search uses +16 for formats 6..10 (las.rs:202-205)
+    s->cls_off = (uint16_t)(query_kind == PCQ_QUERY_BOUNDS ? 15u : cls_offset_in_record(d.format));
     s->rgb_off = (int16_t)rgb_offset_in_record(d.format);
     s->align = field_alignment(rec, d.record_len);
   } else {
@@ -596,8 +601,22 @@ int pcq_ctx_create(int device, pcq_ctx** out) {
   return PCQ_OK;
 }
 
+static void ctx_free(pcq_ctx* ctx);
+
 void pcq_ctx_destroy(pcq_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->refs > 0) {
+    ctx->closing = true;  // freed when the last file / collector goes away
+    return;
+  }
+  ctx_free(ctx);
+}
+
+static void ctx_unref(pcq_ctx* ctx) {
+  if (--ctx->refs == 0 && ctx->closing) ctx_free(ctx);
+}
+
+static void ctx_free(pcq_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (UploadSlot& s : ctx->slots) {
@@ -703,6 +722,7 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
   }
   // the caller may reuse its buffer as soon as we return
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->refs++;
   *out = f;
   return PCQ_OK;
 }
@@ -731,6 +751,7 @@ int pcq_file_wrap_device(pcq_ctx* ctx, const pcq_file_desc* desc, const void* de
     const int rgb_k = rgb_offset_in_record(desc->format);
     f->rgb = rgb_k >= 0 ? base + (uint64_t)rgb_k * N : nullptr;
   }
+  ctx->refs++;
   *out = f;
   return PCQ_OK;
 }
@@ -755,6 +776,7 @@ void pcq_file_release(pcq_file* f) {
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->owned);
   }
+  ctx_unref(f->ctx);
   delete f;
 }
 
@@ -774,6 +796,7 @@ int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const dou
     return fail(PCQ_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(cudaGetLastError()));
   }
   cudaMemsetAsync(c->dev, 0, 256, ctx->stream);
+  ctx->refs++;  // released by pcq_collector_destroy (also on the error paths below)
   if (kind == PCQ_COLLECT_GRID) {
     if (!gmin || !gmax) {
       pcq_collector_destroy(c);
@@ -843,6 +866,7 @@ void pcq_collector_destroy(pcq_collector* c) {
   if (c->d_final) cudaFree(c->d_final);
   if (c->d_export) cudaFree(c->d_export);
   if (c->h_pts) cudaFreeHost(c->h_pts);
+  ctx_unref(c->ctx);
   delete c;
 }
 
@@ -963,7 +987,7 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     RC(plan_file(f->desc, f->raw_format, query, &plan));
     if (plan.skip || f->n_points == 0) continue;
     Segment s;
-    fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base);
+    fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base, query->kind);
     s.first_tile = tile_cursor;
     if (lane_first[lane] == ~0ull) lane_first[lane] = tile_cursor;
     s.lane_first_tile = lane_first[lane];
@@ -1108,7 +1132,7 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
     const int b = (int)(j % kChunkBuffers);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->chunk_copied[b], 0));
     std::vector<Segment> segs(1);
-    fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan, fp.lane, fp.base + pc.first);
+    fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan, fp.lane, fp.base + pc.first, query->kind);
     segs[0].first_tile = 0;
     segs[0].lane_first_tile = 0;
     std::vector<uint64_t> lane_points(n_collectors, 0);

@@ -1,0 +1,188 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol,
+its host-only entry points agree with the oracle, and the synthetic generators are sound.
+No compute entry point is called here (no GPU in this container)."""
+import ctypes as C
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as npo
+from oracle import oracle as orc
+from tests.helpers import make_file
+
+ROOT = Path(__file__).resolve().parent.parent
+KAV = json.loads((Path(__file__).parent / "golden" / "kav.json").read_text())
+
+
+def _desc(pcq, f, layout=0, mask=0):
+    d = pcq.FileDesc()
+    pcq.binding.check(pcq.lib.pcq_parse_header(C.c_void_p(f.ctypes.data), f.nbytes, layout, mask, C.byref(d)))
+    return d
+
+
+def test_library_exports_every_declared_symbol(pcq):
+    declared = set()
+    for hdr in ("pcq.h", "pcq_synth.h"):
+        text = (ROOT / "include" / hdr).read_text()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(pcq_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) > 30
+    out = subprocess.check_output(["nm", "-D", "--defined-only", str(pcq.binding.LIB_PATH)], text=True)
+    exported = set(re.findall(r"\bT (pcq_[a-z0-9_]+)", out))
+    assert declared <= exported, f"missing exports: {sorted(declared - exported)}"
+    assert set(pcq.lib._pcq_symbols) <= exported
+
+
+def test_library_is_sm100a_native(pcq):
+    out = subprocess.run(["cuobjdump", "--list-elf", str(pcq.binding.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_gpu_fails_loudly(pcq):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pcq.PcqError) as e:
+        pcq.Context(0)
+    assert e.value.code == pcq.binding.PCQ_ERR_CUDA and "no CPU fallback" in e.value.message
+
+
+def test_point_layout_is_readers_point(pcq):
+    dt = pcq.POINT_DTYPE  # readers/src/lib.rs:10-19
+    assert dt.itemsize == 31 and dt.fields["pos"][1] == 0 and dt.fields["rgb"][1] == 24 and dt.fields["cls"][1] == 30
+
+
+@pytest.mark.parametrize("k", KAV["local_bounds"], ids=lambda k: k["name"])
+def test_local_bounds_kav(pcq, k):
+    f = make_file(np.zeros((1, 3), np.int32), [0], scale=k["scale"], offset=k["offset"])
+    d = _desc(pcq, f)
+    lo, hi = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+    pcq.binding.check(pcq.lib.pcq_local_bounds(C.byref(d), pcq.binding.d3(k["qmin"]), pcq.binding.d3(k["qmax"]), lo, hi))
+    assert list(lo) == k["lo"] and list(hi) == k["hi"]
+
+
+def test_local_bounds_match_oracle_randomised(pcq):
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        scale = tuple(float(s) for s in rng.choice([0.001, 0.01, 0.00025, 0.0123456789, 1.0, 0.5], size=3))
+        offset = tuple(float(o) for o in rng.uniform(-1e6, 4e6, size=3).round(3))
+        f = make_file(np.zeros((1, 3), np.int32), [0], scale=scale, offset=offset)
+        qmin = rng.uniform(-1e6, 4e6, size=3)
+        qmax = qmin + rng.uniform(0, 1e5, size=3)
+        d = _desc(pcq, f)
+        lo, hi = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        rc = pcq.lib.pcq_local_bounds(C.byref(d), pcq.binding.d3(qmin), pcq.binding.d3(qmax), lo, hi)
+        try:
+            want = orc.local_bounds(orc.parse_header(f), qmin, qmax)
+        except orc.OracleError as e:
+            assert e.code == orc.ORC_ERR_PANIC and rc == pcq.binding.PCQ_ERR_PANIC
+            continue
+        assert rc == 0 and (list(lo), list(hi)) == want
+
+
+@pytest.mark.parametrize("k", KAV["grid_params"], ids=lambda k: k["name"])
+def test_grid_params_kav(pcq, k):
+    dims, bits = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+    pcq.binding.check(pcq.lib.pcq_grid_params(pcq.binding.d3(k["min"]), pcq.binding.d3(k["max"]), k["cell"], dims, bits))
+    assert list(dims) == k["dims"] and list(bits) == k["bits"]
+
+
+def test_grid_params_too_many_cells(pcq):
+    dims, bits = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+    rc = pcq.lib.pcq_grid_params(pcq.binding.d3((0, 0, 0)), pcq.binding.d3((1e9, 1e9, 1e9)), 1e-3, dims, bits)
+    assert rc == pcq.binding.PCQ_ERR_GRID and b"Too many cells" in pcq.lib.pcq_last_error()
+
+
+def test_parse_header_matches_oracle_and_rejects_like_it(pcq):
+    xyz = np.arange(30, dtype=np.int32).reshape(10, 3)
+    for fmt, ver in ((0, (1, 2)), (1, (1, 2)), (2, (1, 2)), (3, (1, 3)), (6, (1, 4)), (7, (1, 4))):
+        f = make_file(xyz, np.arange(10), fmt=fmt, version=ver, scale=(0.001, 0.01, 0.1), offset=(1.5, -2.5, 3.25))
+        d, h = _desc(pcq, f), orc.parse_header(f)
+        assert (d.n_points, d.record_len, d.format, d.point_data_off) == (h.n_points, h.record_len, h.format, h.offset_to_point_data)
+        assert list(d.scale) == list(h.scale) and list(d.offset) == list(h.offset)
+        assert list(d.hdr_min) == list(h.min) and list(d.hdr_max) == list(h.max)
+    f = make_file(xyz, np.arange(10), fmt=1)
+    bad = f.copy()
+    bad[:4] = np.frombuffer(b"LASX", np.uint8)
+    d = pcq.FileDesc()
+    assert pcq.lib.pcq_parse_header(C.c_void_p(bad.ctypes.data), bad.nbytes, 0, 0, C.byref(d)) == pcq.binding.PCQ_ERR_FORMAT
+    assert pcq.lib.pcq_parse_header(C.c_void_p(f.ctypes.data), 100, 0, 0, C.byref(d)) == pcq.binding.PCQ_ERR_IO
+    g = make_file(xyz, np.arange(10), fmt=1, fmt_byte=0x81)
+    assert pcq.lib.pcq_parse_header(C.c_void_p(g.ctypes.data), g.nbytes, 1, 0, C.byref(d)) == pcq.binding.PCQ_ERR_FORMAT
+    assert pcq.lib.pcq_parse_header(C.c_void_p(g.ctypes.data), g.nbytes, 1, 1, C.byref(d)) == 0 and d.format == 1
+    short = make_file(xyz, np.arange(10), fmt=3, record_len=34)
+    short[105] = 20  # record length smaller than format 3 needs
+    assert pcq.lib.pcq_parse_header(C.c_void_p(short.ctypes.data), short.nbytes, 0, 0, C.byref(d)) == pcq.binding.PCQ_ERR_FORMAT
+
+
+def test_file_intersects(pcq):
+    f = make_file(np.array([[0, 0, 0], [100, 100, 100]], np.int32), [1, 1], scale=(1.0,) * 3)
+    d = _desc(pcq, f)
+    out = C.c_int()
+    for qmin, qmax, want in (((100, 100, 100), (200, 200, 200), 1),  # touching faces overlap (closed intervals)
+                             ((100.5, 0, 0), (200, 200, 200), 0), ((-5, -5, -5), (-1, 200, 200), 0), ((50, 50, 50), (60, 60, 60), 1)):
+        pcq.binding.check(pcq.lib.pcq_file_intersects(C.byref(d), pcq.binding.d3(qmin), pcq.binding.d3(qmax), C.byref(out)))
+        assert out.value == want
+    inv = make_file(np.zeros((1, 3), np.int32), [1], hdr_min=(5, 0, 0), hdr_max=(1, 1, 1))
+    rc = pcq.lib.pcq_file_intersects(C.byref(_desc(pcq, inv)), pcq.binding.d3((0, 0, 0)), pcq.binding.d3((1, 1, 1)), C.byref(out))
+    assert rc == pcq.binding.PCQ_ERR_PANIC
+
+
+# ---- synthetic data --------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+def test_synth_las_and_last_hold_the_same_points(pcq, fmt):
+    B, S = pcq.binding, pcq.synth
+    a = S.host_file(S.uniform_spec(2000, B.LAYOUT_LAS, fmt, seed=5))
+    b = S.host_file(S.uniform_spec(2000, B.LAYOUT_LAST, fmt, seed=5))
+    assert np.array_equal(a[:227], b[:227])
+    for klass in (2, 6):
+        assert np.array_equal(npo.search_class(a, "las", klass).view(np.uint8), npo.search_class(b, "last", klass).view(np.uint8))
+    h = orc.parse_header(a)
+    xyz, cls, rgb = npo._columns(a, npo.parse_header(a), "las")
+    pos = xyz.astype(np.float64) * np.array(h.scale[:]) + np.array(h.offset[:])
+    assert np.array_equal(pos.min(axis=0), np.array(h.min[:])) and np.array_equal(pos.max(axis=0), np.array(h.max[:]))
+    assert h.header_size == 227 and h.offset_to_point_data == 227 and (h.version_major, h.version_minor) == (1, 2)
+
+
+def test_synth_is_deterministic_and_seed_sensitive(pcq):
+    B, S = pcq.binding, pcq.synth
+    a = S.host_file(S.uniform_spec(1000, B.LAYOUT_LAS, 1, seed=5))
+    assert np.array_equal(a, S.host_file(S.uniform_spec(1000, B.LAYOUT_LAS, 1, seed=5)))
+    assert not np.array_equal(a, S.host_file(S.uniform_spec(1000, B.LAYOUT_LAS, 1, seed=6)))
+
+
+def test_synth_shapes_and_class_mix(pcq):
+    B, S = pcq.binding, pcq.synth
+    sp = S.doc_specs(n_files=4, pts_per_file=20000)[3]
+    f = S.host_file(sp)
+    h = npo.parse_header(f)
+    xyz, cls, _ = npo._columns(f, h, "las")
+    base = cls & 0x1F
+    frac2 = float((base == 2).mean())
+    assert 0.40 < frac2 < 0.50  # DOC_CLASSES: 45 % ground
+    assert 0.003 < float((cls > 0x1F).mean()) < 0.03  # ~1 % carry a flag bit: whole-byte compare must see them
+    z = xyz[:, 2] * 0.01
+    assert -95 <= z.min() and z.max() <= 195 and 30 < float(np.median(z)) < 70  # bell around 50 m
+    nav = S.host_file(S.navvis_spec(n_points=30000))
+    nx, _, nrgb = npo._columns(nav, npo.parse_header(nav), "las")
+    assert nrgb is not None and len(np.unique(nx[:, 2])) < 20000  # floors: many points share a z level
+    ca = S.host_file(S.ca13_specs(n_files=4, pts_per_file=5000)[0])
+    assert npo.parse_header(ca)["format"] == 1 and len(npo.search_class(ca, "last", 2)) > 2000
+
+
+def test_doc_tiles_cover_the_xl_box_and_boxes_select_tiles(pcq):
+    S = pcq.synth
+    specs = S.doc_specs(n_files=64, pts_per_file=0)
+    hits = {"S": 0, "L": 0, "XL": 0}
+    for sp in specs:
+        x0, y0 = sp.offset[0], sp.offset[1]
+        x1, y1 = x0 + sp.hi[0] * sp.scale[0], y0 + sp.hi[1] * sp.scale[1]
+        for name, (qmin, qmax) in (("S", S.DOC_S), ("L", S.DOC_L), ("XL", S.DOC_XL)):
+            if x0 <= qmax[0] and x1 >= qmin[0] and y0 <= qmax[1] and y1 >= qmin[1]:
+                hits[name] += 1
+    assert hits == {"S": 5, "L": 30, "XL": 64}

@@ -240,3 +240,22 @@ def test_count_parallel_matches_sequential():
         c = orc.Collector(orc.COLLECT_COUNT)
         orc.search_file(f, exts[i], c, bounds=bounds)
         assert c.point_count() == int(got[i])
+
+
+# ---- committed golden fixtures (tests/golden/scan_golden.json; made by tests/golden/make_golden.py) ----
+def test_oracle_reproduces_golden_fixtures(pcq):
+    import hashlib
+
+    from tests.golden.make_golden import CASES, build_case, oracle_answer
+
+    golden = json.loads((Path(__file__).parent / "golden" / "scan_golden.json").read_text())
+    assert set(golden) == set(CASES)
+    for name in CASES:
+        files, exts, kw = build_case(pcq, name)
+        assert hashlib.sha256(b"".join(f.tobytes() for f in files)).hexdigest() == golden[name]["input_sha256"], "generator drifted"
+        got = oracle_answer(files, exts, kw)
+        assert got["counts"] == golden[name]["counts"] and got["buffer_sha256"] == golden[name]["buffer_sha256"]
+        # and the independent numpy restatement agrees with the frozen counts
+        for f, e, want in zip(files, exts, golden[name]["counts"]):
+            p = npo.search_bounds(f, e, *kw["bounds"]) if "bounds" in kw else npo.search_class(f, e, kw["cls"])
+            assert len(p) == want
