@@ -6,7 +6,7 @@ root).  The product is ``libpcq.so`` (csrc/: hand-written sm_100a CUDA kernels b
 include/pcq.h) plus the `query` CLI; this package is the Python twin of the reference's
 Searcher / ResultCollector interface that the tests and bench.py drive it through.
 """
-from . import binding, synth  # noqa: F401
+from . import binding, sharding, synth  # noqa: F401
 from .binding import (  # noqa: F401
     CANDIDATE_DTYPE,
     POINT_DTYPE,
@@ -30,6 +30,7 @@ from .searcher import (  # noqa: F401
     default_context,
     run_search_parallel,
     run_search_sequential,
+    search_host_files_multi,
     search_las_file_by_bounds_optimized,
     search_las_file_by_classification_optimized,
     search_last_file_by_bounds_optimized,

@@ -127,6 +127,7 @@ def _load() -> C.CDLL:
         "pcq_collector_points_device": (C.c_int, [vp, P(vp), P(u64)]),
         "pcq_search_files": (C.c_int, [vp, P(vp), u32, P(Query), P(vp), u32]),
         "pcq_search_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), P(vp), u32]),
+        "pcq_search_host_files_multi": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), u32, P(vp), u32]),
         "pcq_host_alloc": (C.c_int, [sz, P(vp)]),
         "pcq_host_free": (None, [vp]),
         "pcq_grid_export_candidates": (C.c_int, [vp, u32, P(vp), P(u64)]),

@@ -1011,25 +1011,31 @@ void pcq_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-// Host-staged scan: file images stream through a ring of HBM chunk buffers; the copy of chunk k+1
-// overlaps the scan of chunk k.  Replaces mmap + page-fault driven reads (las.rs:24-31).
-int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
-                          uint32_t n_files, const pcq_query* query, pcq_collector* const* collectors,
-                          uint32_t n_collectors) {
-  RC(check_search_args(ctx, n_files, query, collectors, n_collectors));
+// Host-staged scan: file images stream through a ring of HBM chunk buffers; the copy of chunk k+2
+// overlaps the scan of chunk k.  Replaces mmap + page-fault driven reads (las.rs:24-31).  Several
+// queries can share one pass: every chunk is scanned by each query that needs its file while it is
+// resident, so the bytes cross PCIe once per batch instead of once per query.
+static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
+                             uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                             pcq_collector* const* collectors, uint32_t n_collectors) {
+  if (n_queries == 0) return PCQ_OK;
+  for (uint32_t q = 0; q < n_queries; ++q)
+    RC(check_search_args(ctx, n_files, queries + q, collectors + (size_t)q * n_collectors, n_collectors));
   if (n_files == 0) return PCQ_OK;
   if (!file_bytes || !n_bytes || !exts) return fail(PCQ_ERR_ARG, "null argument");
   RC(use_device(ctx));
-  const int kind = collectors[0]->kind;
 
   size_t chunk_bytes = 64u << 20;
   if (const char* e = std::getenv("PCQ_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  if (ctx->chunk_cap < chunk_bytes) {
+  if (ctx->chunk_cap != chunk_bytes) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     for (int b = 0; b < kChunkBuffers; ++b) {
       if (ctx->chunk[b]) cudaFree(ctx->chunk[b]);
       ctx->chunk[b] = nullptr;
     }
+    ctx->chunk_cap = 0;
     for (int b = 0; b < kChunkBuffers; ++b) CU(cudaMalloc(&ctx->chunk[b], chunk_bytes + 1024));
     ctx->chunk_cap = chunk_bytes;
   }
@@ -1038,7 +1044,6 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
     if (!ctx->chunk_free[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_free[b], cudaEventDisableTiming));
   }
 
-  // plan: one entry per (file, point range)
   struct Piece {
     uint32_t file;
     uint64_t first, n;
@@ -1046,10 +1051,10 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
   struct FilePlan {
     pcq_file_desc d;
     uint8_t raw;
-    SegmentPlan plan;
-    uint64_t base;
+    std::vector<SegmentPlan> plan;  // per query
+    std::vector<uint64_t> base;     // per query: scan index of the file's point 0 in its collector
     uint32_t lane;
-    bool need_pos, need_cls, need_rgb;
+    bool any, need_pos, need_cls, need_rgb;
   };
   std::vector<FilePlan> fps(n_files);
   std::vector<Piece> pieces;
@@ -1061,15 +1066,25 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
     if ((uint64_t)fp.d.point_data_off + fp.d.n_points * (uint64_t)fp.d.record_len > (uint64_t)n_bytes[i])
       return fail(PCQ_ERR_IO, "file image %u is shorter than its header promises", i);
     fp.lane = n_collectors == 1 ? 0 : i;
-    pcq_collector* c = collectors[fp.lane];
-    fp.base = c->scan_total;
-    c->scan_total += fp.d.n_points;
-    RC(plan_file(fp.d, fp.raw, query, &fp.plan));
-    if (fp.plan.skip || fp.d.n_points == 0) continue;
-    const bool emit = kind != PCQ_COLLECT_COUNT;
-    fp.need_pos = query->kind == PCQ_QUERY_BOUNDS || emit;
-    fp.need_cls = query->kind == PCQ_QUERY_CLASS || emit;
-    fp.need_rgb = emit && rgb_offset_in_record(fp.d.format) >= 0;
+    fp.plan.resize(n_queries);
+    fp.base.resize(n_queries);
+    fp.any = fp.need_pos = fp.need_cls = fp.need_rgb = false;
+    for (uint32_t q = 0; q < n_queries; ++q) {
+      pcq_collector* c = collectors[(size_t)q * n_collectors + fp.lane];
+      fp.base[q] = c->scan_total;
+      c->scan_total += fp.d.n_points;
+      RC(plan_file(fp.d, fp.raw, queries + q, &fp.plan[q]));
+      if (fp.plan[q].skip || fp.d.n_points == 0) {
+        fp.plan[q].skip = true;
+        continue;
+      }
+      const bool emit = c->kind != PCQ_COLLECT_COUNT;
+      fp.any = true;
+      fp.need_pos |= queries[q].kind == PCQ_QUERY_BOUNDS || emit;
+      fp.need_cls |= queries[q].kind == PCQ_QUERY_CLASS || emit;
+      fp.need_rgb |= emit && rgb_offset_in_record(fp.d.format) >= 0;
+    }
+    if (!fp.any) continue;
     uint64_t per_point = layout == PCQ_LAYOUT_LAS
                              ? fp.d.record_len
                              : (fp.need_pos ? 12 : 0) + (fp.need_cls ? 1 : 0) + (fp.need_rgb ? 6 : 0);
@@ -1125,23 +1140,43 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
   for (int b = 0; b < kChunkBuffers; ++b) CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   const size_t prefetch = kChunkBuffers - 1;
   for (size_t j = 0; j < std::min(prefetch, pieces.size()); ++j) RC(issue_copy(j));
+  std::vector<Segment> segs(1);
+  std::vector<uint64_t> lane_points(n_collectors, 0);
   for (size_t j = 0; j < pieces.size(); ++j) {
     if (j + prefetch < pieces.size()) RC(issue_copy(j + prefetch));
     const Piece& pc = pieces[j];
     const FilePlan& fp = fps[pc.file];
     const int b = (int)(j % kChunkBuffers);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->chunk_copied[b], 0));
-    std::vector<Segment> segs(1);
-    fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan, fp.lane, fp.base + pc.first, query->kind);
-    segs[0].first_tile = 0;
-    segs[0].lane_first_tile = 0;
-    std::vector<uint64_t> lane_points(n_collectors, 0);
-    lane_points[fp.lane] = pc.n;
-    // run_batch indexes lanes by Segment::lane, so hand it the full collector array
-    RC(run_batch(ctx, segs, (pc.n + kTilePts - 1) / kTilePts, query, collectors, n_collectors, lane_points));
+    for (uint32_t q = 0; q < n_queries; ++q) {
+      if (fp.plan[q].skip) continue;
+      fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan[q], fp.lane,
+                   fp.base[q] + pc.first, queries[q].kind);
+      segs[0].first_tile = 0;
+      segs[0].lane_first_tile = 0;
+      std::fill(lane_points.begin(), lane_points.end(), 0);
+      lane_points[fp.lane] = pc.n;
+      // run_batch indexes lanes by Segment::lane, so hand it the query's full collector array
+      RC(run_batch(ctx, segs, (pc.n + kTilePts - 1) / kTilePts, queries + q, collectors + (size_t)q * n_collectors,
+                   n_collectors, lane_points));
+    }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }
   return PCQ_OK;
+}
+
+int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
+                          uint32_t n_files, const pcq_query* query, pcq_collector* const* collectors,
+                          uint32_t n_collectors) {
+  if (!query) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, query, 1, collectors, n_collectors);
+}
+
+int pcq_search_host_files_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
+                                const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                                pcq_collector* const* collectors, uint32_t n_collectors_per_query) {
+  if (!queries && n_queries) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query);
 }
 
 // ---- multi-GPU density exchange --------------------------------------------------------------------

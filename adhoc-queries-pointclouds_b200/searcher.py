@@ -272,6 +272,21 @@ class Searcher:
         check(lib.pcq_search_host_files(ctx.handle, ptrs, sizes, exts, n, C.byref(q), ch, len(collectors)))
 
 
+def search_host_files_multi(images: Sequence[tuple], searchers: Sequence["Searcher"],
+                            collectors_per_query: Sequence[Sequence[ResultCollector]]) -> None:
+    """One host-staged pass for several queries (pcq_search_host_files_multi): the file images cross PCIe once."""
+    ctx = collectors_per_query[0][0].ctx
+    n, nq, ncol = len(images), len(searchers), len(collectors_per_query[0])
+    assert all(len(c) == ncol for c in collectors_per_query) and len(collectors_per_query) == nq
+    addrs = [B.buffer_address(b) for b, _ in images]
+    ptrs = (C.c_void_p * n)(*[a for a, _ in addrs])
+    sizes = (C.c_size_t * n)(*[s for _, s in addrs])
+    exts = (C.c_char_p * n)(*[e.encode() for _, e in images])
+    qs = (B.Query * nq)(*[s._query() for s in searchers])
+    ch = (C.c_void_p * (nq * ncol))(*[c.handle for cs in collectors_per_query for c in cs])
+    check(lib.pcq_search_host_files_multi(ctx.handle, ptrs, sizes, exts, n, qs, nq, ch, ncol))
+
+
 class BoundsSearcher(Searcher):
     """BoundsSearcher::new(bounds) (searcher.rs:33-41); bounds = (min xyz, max xyz)."""
 

@@ -192,6 +192,13 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
                           const char* const* exts, uint32_t n_files, const pcq_query* query,
                           pcq_collector* const* collectors, uint32_t n_collectors);
 
+/* Same, for a batch of queries over the same files: every chunk that crosses PCIe is scanned by each
+ * query that needs its file while it is resident.  collectors[q * n_collectors_per_query + lane] is
+ * the collector of query q (lane = 0 for sequential mode, = file index for parallel mode). */
+int pcq_search_host_files_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
+                                const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                                pcq_collector* const* collectors, uint32_t n_collectors_per_query);
+
 /* Pinned host memory helpers for callers that want full-speed staging. */
 int pcq_host_alloc(size_t n_bytes, void** out);
 void pcq_host_free(void* p);
