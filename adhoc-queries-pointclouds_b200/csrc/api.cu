@@ -433,10 +433,10 @@ int grid_finalize(pcq_collector* c) {
 }
 
 // one kernel launch for a prepared batch of segments; handles BUFFER / GRID capacity retries
-int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, uint64_t n_tiles, const pcq_query* q,
-              pcq_collector* const* collectors, uint32_t n_collectors, const std::vector<uint64_t>& lane_points) {
+int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_collector* const* collectors,
+              uint32_t n_collectors, const std::vector<uint64_t>& lane_points) {
   const int kind = collectors[0]->kind;
-  if (segs.empty() || n_tiles == 0) return PCQ_OK;
+  if (segs.empty()) return PCQ_OK;
 
   // kernel variant: staged needs one record length, 16-byte aligned ranges, and records that carry
   // the predicate's field (LAST class queries read the class column -> direct)
@@ -455,6 +455,20 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, uint64_t n_tiles, const 
 
   std::vector<LaneDev> lanes(n_collectors);
   const int mode = kind == PCQ_COLLECT_COUNT ? MODE_COUNT : (kind == PCQ_COLLECT_BUFFER ? MODE_SELECT : MODE_GRID);
+
+  // number the scheduling units ("tiles") across the segments of the launch; lanes are contiguous runs
+  const uint32_t tile_pts = tile_points(variant, mode, R);
+  uint64_t n_tiles = 0;
+  {
+    std::vector<uint64_t> lane_first(n_collectors, ~0ull);
+    for (Segment& s : segs) {
+      s.first_tile = n_tiles;
+      if (lane_first[s.lane] == ~0ull) lane_first[s.lane] = n_tiles;
+      s.lane_first_tile = lane_first[s.lane];
+      n_tiles += (s.n_points + tile_pts - 1) / tile_pts;
+    }
+  }
+  if (n_tiles == 0) return PCQ_OK;
 
   if (kind == PCQ_COLLECT_BUFFER) {
     for (uint32_t l = 0; l < n_collectors; ++l) {
@@ -495,6 +509,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, uint64_t n_tiles, const 
     P.query_kind = q->kind;
     P.cls = q->cls;
     P.n_tiles = n_tiles;
+    P.tile_pts = tile_pts;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
     if (mode == MODE_SELECT) {
       RC(ensure_tile_state(ctx, n_tiles));
@@ -973,8 +988,6 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
   std::vector<Segment> segs;
   segs.reserve(n_files);
   std::vector<uint64_t> lane_points(n_collectors, 0);
-  std::vector<uint64_t> lane_first(n_collectors, ~0ull);
-  uint64_t tile_cursor = 0;
   for (uint32_t i = 0; i < n_files; ++i) {
     pcq_file* f = files[i];
     if (!f) return fail(PCQ_ERR_ARG, "null file %u", i);
@@ -988,14 +1001,10 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     if (plan.skip || f->n_points == 0) continue;
     Segment s;
     fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base, query->kind);
-    s.first_tile = tile_cursor;
-    if (lane_first[lane] == ~0ull) lane_first[lane] = tile_cursor;
-    s.lane_first_tile = lane_first[lane];
-    tile_cursor += (f->n_points + kTilePts - 1) / kTilePts;
     lane_points[lane] += f->n_points;
     segs.push_back(s);
   }
-  return run_batch(ctx, segs, tile_cursor, query, collectors, n_collectors, lane_points);
+  return run_batch(ctx, segs, query, collectors, n_collectors, lane_points);
 }
 
 int pcq_host_alloc(size_t n_bytes, void** out) {
@@ -1152,13 +1161,10 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       if (fp.plan[q].skip) continue;
       fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan[q], fp.lane,
                    fp.base[q] + pc.first, queries[q].kind);
-      segs[0].first_tile = 0;
-      segs[0].lane_first_tile = 0;
       std::fill(lane_points.begin(), lane_points.end(), 0);
       lane_points[fp.lane] = pc.n;
       // run_batch indexes lanes by Segment::lane, so hand it the query's full collector array
-      RC(run_batch(ctx, segs, (pc.n + kTilePts - 1) / kTilePts, queries + q, collectors + (size_t)q * n_collectors,
-                   n_collectors, lane_points));
+      RC(run_batch(ctx, segs, queries + q, collectors + (size_t)q * n_collectors, n_collectors, lane_points));
     }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }

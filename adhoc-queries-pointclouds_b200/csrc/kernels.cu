@@ -278,8 +278,9 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Executed by all 32 lanes of warp 0.  Returns the number of matches in tiles
-// [lane_first_tile, tile) — the exclusive prefix of `tile` within its lane.
+// Executed by all 32 lanes of warp 0.  Returns the number of matches in units
+// [lane_first_tile, tile) — the exclusive prefix of `tile` within its lane.  Every lane inspects
+// four descriptors per round trip (window of 128 units), closest units in the lowest lanes.
 __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* state, uint64_t tile,
                                                                  uint64_t lane_first_tile) {
   unsigned long long excl = 0;
@@ -287,23 +288,34 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
   const long long lo = (long long)lane_first_tile;
   const uint32_t ln = lane_id();
   while (hi >= lo) {
-    long long t = hi - (long long)ln;
-    const bool valid = t >= lo;
-    unsigned long long s;
+    unsigned long long sv[4];
+    bool pending;
     do {
-      s = valid ? ld_state(state + t) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
-    } while (__any_sync(0xffffffffu, (s >> kStatusShift) == 0ull));
-    const uint32_t pm = __ballot_sync(0xffffffffu, (s >> kStatusShift) == kStPrefix);
-    unsigned long long v = s & kValueMask;
-    if (pm != 0u) {
-      const uint32_t first = (uint32_t)__ffs((int)pm) - 1u;  // closest tile that already has its prefix
-      if (ln > first) v = 0ull;
+      pending = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long t = hi - (long long)(4u * ln + (uint32_t)k);
+        sv[k] = t >= lo ? ld_state(state + t) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
+        pending |= (sv[k] >> kStatusShift) == 0ull;
+      }
+    } while (__any_sync(0xffffffffu, pending));
+    int kf = 4;  // first (closest) descriptor of this lane that already carries an inclusive prefix
+#pragma unroll
+    for (int k = 3; k >= 0; --k)
+      if ((sv[k] >> kStatusShift) == kStPrefix) kf = k;
+    const uint32_t pm = __ballot_sync(0xffffffffu, kf < 4);
+    const uint32_t first = pm ? (uint32_t)__ffs((int)pm) - 1u : 32u;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool take = ln < first || (ln == first && k <= kf);
+      if (take) v += sv[k] & kValueMask;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     excl += v;
     if (pm != 0u) break;
-    hi -= 32;
+    hi -= 128;
   }
   return excl;
 }
@@ -381,8 +393,14 @@ __device__ __forceinline__ void grid_insert(const GridDev& g, const Segment& S, 
       if (slot == ~0ull) {
         atomicOr(g.flags, kFlagHashFull);
       } else {
-        unsigned long long old = atomicMin(g.table + slot, e.dist_bits);
-        want = e.dist_bits <= old;
+        // The cell minimum only ever decreases, so a (possibly stale) plain read that is already smaller than
+        // this point's distance proves the point can never win: skip the atomic.  In dense data (many points
+        // per cell) that removes most of the read-modify-write traffic.
+        const unsigned long long seen = __ldcg(g.table + slot);
+        if (e.dist_bits <= seen) {
+          const unsigned long long old = atomicMin(g.table + slot, e.dist_bits);
+          want = e.dist_bits <= old;
+        }
       }
     }
   }
@@ -412,20 +430,8 @@ __device__ __forceinline__ void grid_insert(const GridDev& g, const Segment& S, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-tile work shared by the direct and the staged scan kernels
+// per-tile work shared by the direct and the staged scan kernels (MODE_COUNT / MODE_GRID)
 // ------------------------------------------------------------------------------------------------
-struct SelectShared {
-  uint32_t warp_cnt[kPPT][kBlock / 32];
-  unsigned long long out_rec;  // lane.out_base + exclusive prefix of this tile
-  alignas(16) uint8_t stage[kTilePts * 31 + 32];
-};
-
-// only MODE_SELECT kernels pay for the output staging buffer
-template <int MODE>
-struct alignas(16) SelectStorage {
-  uint8_t bytes[MODE == MODE_SELECT ? sizeof(SelectShared) : 16];
-};
-
 __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* scratch /* kBlock/32 */) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -440,7 +446,8 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 
 template <int MODE, class Src>
 __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment& S, uint64_t tile, const Src& src,
-                                             unsigned long long& acc, SelectShared* sel) {
+                                             unsigned long long& acc) {
+  static_assert(MODE == MODE_COUNT || MODE == MODE_GRID, "select has its own kernels");
   const uint64_t p0 = (tile - S.first_tile) * (uint64_t)kTilePts;
   const uint64_t rem = S.n_points - p0;
   const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
@@ -458,83 +465,13 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment&
   if constexpr (MODE == MODE_COUNT) {
 #pragma unroll
     for (int j = 0; j < kPPT; ++j) acc += m[j] ? 1ull : 0ull;
-    return;
-  } else if constexpr (MODE == MODE_GRID) {
+  } else {
     const GridDev& g = P.lanes[S.lane].grid;
 #pragma unroll
     for (int j = 0; j < kPPT; ++j) {
       const uint32_t i = (uint32_t)j * kBlock + tid;
       grid_insert(g, S, src, m[j], h[j], p0 + i, i);
     }
-    return;
-  } else {
-    // ---- MODE_SELECT: BufferCollector::collect_one in scan order ----
-    const LaneDev& L = P.lanes[S.lane];
-    uint32_t bal[kPPT];
-#pragma unroll
-    for (int j = 0; j < kPPT; ++j) {
-      bal[j] = __ballot_sync(0xffffffffu, m[j]);
-      if (lane_id() == 0) sel->warp_cnt[j][warp_id()] = (uint32_t)__popc(bal[j]);
-    }
-    __syncthreads();
-    uint32_t total = 0;
-    uint32_t my_off[kPPT];
-#pragma unroll
-    for (int j = 0; j < kPPT; ++j) {
-      my_off[j] = 0;
-#pragma unroll
-      for (int w = 0; w < kBlock / 32; ++w) {
-        const uint32_t c = sel->warp_cnt[j][w];
-        if (w == (int)warp_id()) my_off[j] = total + (uint32_t)__popc(bal[j] & ((1u << lane_id()) - 1u));
-        total += c;
-      }
-    }
-    if (warp_id() == 0) {
-      unsigned long long excl = 0;
-      const bool first = tile == S.lane_first_tile;
-      if (!first) {
-        if (lane_id() == 0) st_state(P.tile_state + tile, (kStAgg << kStatusShift) | (unsigned long long)total);
-        excl = lookback_exclusive(P.tile_state, tile, S.lane_first_tile);
-      }
-      if (lane_id() == 0) {
-        st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
-        sel->out_rec = L.out_base + excl;
-        if (total) atomicAdd(L.count, (unsigned long long)total);
-      }
-    }
-    __syncthreads();
-    const unsigned long long out_rec = sel->out_rec;
-    const unsigned long long gb0 = out_rec * 31ull;          // first output byte of this tile
-    const uint32_t so = (uint32_t)(gb0 & 15ull);             // keep global and shared 16-byte phases equal
-#pragma unroll
-    for (int j = 0; j < kPPT; ++j) {
-      if (m[j]) {
-        const uint32_t i = (uint32_t)j * kBlock + tid;
-        uint32_t rgb[3];
-        src.colour(S, p0 + i, i, rgb);
-        uint32_t w[8];
-        point_words(S, h[j], rgb, w);
-        sts_point31(sel->stage + so + my_off[j] * 31u, w);
-      }
-    }
-    __syncthreads();
-    // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
-    unsigned long long room = out_rec < L.out_cap ? L.out_cap - out_rec : 0ull;
-    const uint32_t n_ok = room < (unsigned long long)total ? (uint32_t)room : total;
-    const uint32_t nb = n_ok * 31u;
-    if (nb) {
-      uint8_t* gout = L.out + gb0;  // byte address of stage[so]
-      uint32_t head = (16u - so) & 15u;
-      if (head > nb) head = nb;
-      const uint32_t nvec = (nb - head) >> 4;
-      const uint32_t tail0 = head + (nvec << 4);
-      if (tid < head) gout[tid] = sel->stage[so + tid];
-      const uint4* svec = reinterpret_cast<const uint4*>(sel->stage + so + head);
-      uint4* gvec = reinterpret_cast<uint4*>(gout + head);
-      for (uint32_t k = tid; k < nvec; k += kBlock) gvec[k] = svec[k];
-      if (tid < nb - tail0) gout[tail0 + tid] = sel->stage[so + tail0 + tid];
-    }
-    __syncthreads();  // staging buffer is reused by the next tile
   }
 }
 
@@ -544,11 +481,7 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment&
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
   __shared__ Segment sseg;
-  __shared__ unsigned long long s_tile;
   __shared__ unsigned long long s_red[kBlock / 32];
-  __shared__ SelectStorage<MODE> s_sel_storage;
-  SelectShared* sel = nullptr;
-  if constexpr (MODE == MODE_SELECT) sel = reinterpret_cast<SelectShared*>(&s_sel_storage);
 
   uint32_t seg_i = 0xFFFFFFFFu;
   uint32_t seg_cursor = 0;
@@ -556,15 +489,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
   DirectSrc src;
 
   for (uint64_t iter = 0;; ++iter) {
-    uint64_t tile;
-    if constexpr (MODE == MODE_SELECT) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_tile = atomicAdd(P.ticket, 1ull);
-      __syncthreads();
-      tile = s_tile;
-    } else {
-      tile = (uint64_t)blockIdx.x + iter * (uint64_t)gridDim.x;
-    }
+    const uint64_t tile = (uint64_t)blockIdx.x + iter * (uint64_t)gridDim.x;
     if (tile >= P.n_tiles) break;
     while (seg_cursor + 1 < P.n_segs && tile >= P.segs[seg_cursor + 1].first_tile) ++seg_cursor;
     if (seg_cursor != seg_i) {
@@ -583,7 +508,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
       seg_i = seg_cursor;
       __syncthreads();
     }
-    process_tile<MODE>(P, sseg, tile, src, acc, sel);
+    process_tile<MODE>(P, sseg, tile, src, acc);
   }
   if constexpr (MODE == MODE_COUNT) {
     if (seg_i != 0xFFFFFFFFu) {
@@ -637,9 +562,6 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
   __shared__ uint32_t stage_seg[STAGES];
   __shared__ Segment sseg;
   __shared__ unsigned long long s_red[kBlock / 32];
-  __shared__ SelectStorage<MODE> s_sel_storage;
-  SelectShared* sel = nullptr;
-  if constexpr (MODE == MODE_SELECT) sel = reinterpret_cast<SelectShared*>(&s_sel_storage);
 
   const uint32_t tid = threadIdx.x;
   // producer state (meaningful in thread 0 only)
@@ -647,12 +569,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
   uint64_t prod_iter = 0;
 
   auto produce = [&](int s) {
-    uint64_t tile;
-    if constexpr (MODE == MODE_SELECT) {
-      tile = atomicAdd(P.ticket, 1ull);  // tickets keep tile order == issue order (look-back progress)
-    } else {
-      tile = (uint64_t)blockIdx.x + prod_iter * (uint64_t)gridDim.x;
-    }
+    const uint64_t tile = (uint64_t)blockIdx.x + prod_iter * (uint64_t)gridDim.x;
     ++prod_iter;
     if (tile >= P.n_tiles) {
       stage_tile[s] = ~0ull;
@@ -707,7 +624,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     }
     mbar_wait(&full_bar[s], parity);
     SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
-    process_tile<MODE>(P, sseg, tile, src, acc, sel);
+    process_tile<MODE>(P, sseg, tile, src, acc);
     __syncthreads();  // every thread is done reading stage s
     if (tid == 0) produce((int)s);
   }
@@ -715,6 +632,284 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     if (seg_i != 0xFFFFFFFFu) {
       unsigned long long t = block_sum(acc, s_red);
       if (tid == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MODE_SELECT — BufferCollector::collect_one in scan order (collect_points.rs:29-31): single-pass
+// stable stream compaction.
+//
+// The unit of the decoupled look-back is a GROUP of up to kMaxGroup sub-tiles (512 records each)
+// handled by one CTA: (1) count phase — evaluate every sub-tile, keep per-warp match counts in
+// shared memory; (2) publish the unit's aggregate, take the ticket of the NEXT unit, look back
+// over earlier units for the exclusive prefix; (3) emit phase — re-evaluate each sub-tile, compose
+// its matching 31-byte records contiguously in shared memory and flush them with 16-byte stores.
+// At 6.5 TB/s a 512-record tile lasts ~2 ns, far shorter than one L2 round trip; 2-4 K-record units
+// keep the number of unresolved predecessors within one or two 128-wide look-back windows.
+// Tickets (not blockIdx) order the units, so a unit only ever waits for units held by running CTAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGroup = 8;
+
+struct SelectShared {
+  uint32_t warp_cnt[kMaxGroup][kPPT][kBlock / 32];
+  unsigned long long out_rec;   // lane.out_base + exclusive prefix of the current unit
+  unsigned long long cur_tile;  // direct kernel: ticket broadcast
+  alignas(16) uint8_t stage[kTilePts * 31 + 32];
+};
+
+template <class Src>
+__device__ __forceinline__ void select_count_sub(const ScanParams& P, const Segment& S, const Src& src, uint64_t p0,
+                                                 uint32_t npts, uint32_t (*warp_cnt)[kBlock / 32]) {
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
+    Hit h;
+    bool m = false;
+    if (i < npts) m = src.template eval<false>(S, P.query_kind, P.cls, p0 + i, i, h);
+    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+    if (lane_id() == 0) warp_cnt[j][warp_id()] = (uint32_t)__popc(bal);
+  }
+}
+
+// all sub-tile counts of the unit are in shared memory (and synchronised) when this runs;
+// returns the number of matches of the sub-tile
+template <class Src>
+__device__ __forceinline__ uint32_t select_emit_sub(const ScanParams& P, const Segment& S, const LaneDev& L, const Src& src,
+                                                    uint64_t p0, uint32_t npts, const uint32_t (*warp_cnt)[kBlock / 32],
+                                                    unsigned long long out_rec, SelectShared* sel) {
+  const uint32_t tid = threadIdx.x;
+  Hit h[kPPT];
+  bool m[kPPT];
+  uint32_t my_off[kPPT];
+  uint32_t total = 0;
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    const uint32_t i = (uint32_t)j * kBlock + tid;
+    m[j] = false;
+    if (i < npts) m[j] = src.template eval<true>(S, P.query_kind, P.cls, p0 + i, i, h[j]);
+    const uint32_t bal = __ballot_sync(0xffffffffu, m[j]);
+    my_off[j] = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) {
+      const uint32_t c = warp_cnt[j][w];
+      if (w == (int)warp_id()) my_off[j] = total + (uint32_t)__popc(bal & ((1u << lane_id()) - 1u));
+      total += c;
+    }
+  }
+  if (total == 0) {  // uniform: nothing to write for this sub-tile
+    __syncthreads();  // ... but every thread must be done reading the stage before the caller refills it
+    return 0;
+  }
+  const unsigned long long gb0 = out_rec * 31ull;     // first output byte of this sub-tile
+  const uint32_t so = (uint32_t)(gb0 & 15ull);        // keep global and shared 16-byte phases equal
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    if (m[j]) {
+      const uint32_t i = (uint32_t)j * kBlock + tid;
+      uint32_t rgb[3];
+      src.colour(S, p0 + i, i, rgb);
+      uint32_t w[8];
+      point_words(S, h[j], rgb, w);
+      sts_point31(sel->stage + so + my_off[j] * 31u, w);
+    }
+  }
+  __syncthreads();
+  // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
+  const unsigned long long room = out_rec < L.out_cap ? L.out_cap - out_rec : 0ull;
+  const uint32_t n_ok = room < (unsigned long long)total ? (uint32_t)room : total;
+  const uint32_t nb = n_ok * 31u;
+  if (nb) {
+    uint8_t* gout = L.out + gb0;  // byte address of stage[so]
+    uint32_t head = (16u - so) & 15u;
+    if (head > nb) head = nb;
+    const uint32_t nvec = (nb - head) >> 4;
+    const uint32_t tail0 = head + (nvec << 4);
+    if (tid < head) gout[tid] = sel->stage[so + tid];
+    const uint4* svec = reinterpret_cast<const uint4*>(sel->stage + so + head);
+    uint4* gvec = reinterpret_cast<uint4*>(gout + head);
+    for (uint32_t k = tid; k < nvec; k += kBlock) gvec[k] = svec[k];
+    if (tid < nb - tail0) gout[tail0 + tid] = sel->stage[so + tail0 + tid];
+  }
+  __syncthreads();  // the staging buffer is reused by the next sub-tile
+  return total;
+}
+
+// sum of all sub-tile counts of a unit (uniform across the CTA)
+__device__ __forceinline__ uint32_t select_unit_total(const SelectShared* sel, uint32_t n_sub) {
+  uint32_t total = 0;
+  for (uint32_t j = 0; j < n_sub; ++j)
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k)
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) total += sel->warp_cnt[j][k][w];
+  return total;
+}
+
+// warp 0: publish the unit's aggregate / prefix, resolve its exclusive prefix, bump the lane's count
+__device__ __forceinline__ void select_publish(const ScanParams& P, const Segment& S, const LaneDev& L, uint64_t tile,
+                                               uint32_t total, SelectShared* sel) {
+  unsigned long long excl = 0;
+  const bool first = tile == S.lane_first_tile;
+  if (!first) {
+    if (lane_id() == 0) st_state(P.tile_state + tile, (kStAgg << kStatusShift) | (unsigned long long)total);
+    excl = lookback_exclusive(P.tile_state, tile, S.lane_first_tile);
+  }
+  if (lane_id() == 0) {
+    st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
+    sel->out_rec = L.out_base + excl;
+    if (total) atomicAdd(L.count, (unsigned long long)total);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_select_direct(ScanParams P) {
+  __shared__ Segment sseg;
+  __shared__ SelectShared sel;
+  uint32_t seg_i = 0xFFFFFFFFu, seg_cursor = 0;
+  DirectSrc src;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sel.cur_tile = atomicAdd(P.ticket, 1ull);
+    __syncthreads();
+    const uint64_t tile = sel.cur_tile;
+    if (tile >= P.n_tiles) break;
+    while (seg_cursor + 1 < P.n_segs && tile >= P.segs[seg_cursor + 1].first_tile) ++seg_cursor;
+    if (seg_cursor != seg_i) {
+      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_cursor);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&sseg);
+      for (uint32_t k = threadIdx.x; k < sizeof(Segment) / 4; k += kBlock) dstw[k] = srcw[k];
+      seg_i = seg_cursor;
+      __syncthreads();
+    }
+    const Segment& S = sseg;
+    const LaneDev& L = P.lanes[S.lane];
+    const uint64_t u0 = (tile - S.first_tile) * (uint64_t)P.tile_pts;
+    const uint64_t rem = S.n_points - u0;
+    const uint32_t unit_pts = rem < (uint64_t)P.tile_pts ? (uint32_t)rem : P.tile_pts;
+    const uint32_t n_sub = (unit_pts + kTilePts - 1) / kTilePts;
+    for (uint32_t j = 0; j < n_sub; ++j) {
+      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
+      select_count_sub(P, S, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j]);
+    }
+    __syncthreads();
+    const uint32_t total = select_unit_total(&sel, n_sub);
+    if (warp_id() == 0) select_publish(P, S, L, tile, total, &sel);
+    __syncthreads();
+    unsigned long long run = sel.out_rec;
+    if (total == 0) continue;
+    for (uint32_t j = 0; j < n_sub; ++j) {
+      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
+      run += select_emit_sub(P, S, L, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j], run, &sel);
+    }
+  }
+}
+
+// staged variant: the G sub-tiles of a unit are the G stages of the bulk-copy ring
+template <int R, int G>
+__global__ void __launch_bounds__(kBlock) k_select_staged(ScanParams P) {
+  static_assert(G <= kMaxGroup, "group larger than the count table");
+  constexpr uint32_t kSubBytes = (uint32_t)kTilePts * (uint32_t)R;
+  extern __shared__ __align__(128) uint8_t dsm[];  // G * kSubBytes
+  __shared__ __align__(8) uint64_t full_bar[G];
+  __shared__ Segment sseg;
+  __shared__ SelectShared sel;
+  struct Next {
+    unsigned long long tile;  // ~0 = no more units
+    const uint8_t* src;       // first record of the unit
+    uint32_t npts;
+    uint32_t seg;
+  };
+  __shared__ Next nxt;
+
+  const uint32_t tid = threadIdx.x;
+  uint32_t prod_seg = 0;  // thread 0 only
+
+  auto take_ticket = [&]() {
+    const unsigned long long tile = atomicAdd(P.ticket, 1ull);
+    if (tile >= P.n_tiles) {
+      nxt.tile = ~0ull;
+      return;
+    }
+    while (prod_seg + 1 < P.n_segs && tile >= P.segs[prod_seg + 1].first_tile) ++prod_seg;
+    const Segment* sg = P.segs + prod_seg;
+    const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)P.tile_pts;
+    const uint64_t rem = sg->n_points - u0;
+    nxt.tile = tile;
+    nxt.src = sg->rec + u0 * (uint64_t)R;
+    nxt.npts = rem < (uint64_t)P.tile_pts ? (uint32_t)rem : P.tile_pts;
+    nxt.seg = prod_seg;
+  };
+  // load sub-tile j of the NEXT unit into stage j (thread 0)
+  auto issue = [&](uint32_t j) {
+    if (nxt.tile == ~0ull) return;
+    const uint32_t off = j * (uint32_t)kTilePts;
+    if (off >= nxt.npts) return;
+    const uint32_t n = min((uint32_t)kTilePts, nxt.npts - off);
+    const uint32_t bytes = (n * (uint32_t)R + 15u) & ~15u;
+    mbar_arrive_expect_tx(&full_bar[j], bytes);
+    bulk_copy_g2s(dsm + (size_t)j * kSubBytes, nxt.src + (uint64_t)off * R, bytes, &full_bar[j]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) mbar_init(&full_bar[j], 1u);
+    mbar_fence_init();
+    take_ticket();
+#pragma unroll 1
+    for (uint32_t j = 0; j < (uint32_t)G; ++j) issue(j);
+  }
+  __syncthreads();
+
+  uint32_t parity = 0;  // bit j: parity of the next completion of stage j
+  uint32_t seg_i = 0xFFFFFFFFu;
+  for (;;) {
+    const unsigned long long tile = nxt.tile;
+    if (tile == ~0ull) break;
+    const uint32_t unit_pts = nxt.npts;
+    const uint32_t seg_now = nxt.seg;
+    if (seg_now != seg_i) {
+      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_now);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&sseg);
+      for (uint32_t k = tid; k < sizeof(Segment) / 4; k += kBlock) dstw[k] = srcw[k];
+      seg_i = seg_now;
+    }
+    __syncthreads();  // everyone has read nxt (thread 0 overwrites it below); sseg is complete
+    const Segment& S = sseg;
+    const LaneDev& L = P.lanes[S.lane];
+    const uint64_t u0 = (tile - S.first_tile) * (uint64_t)P.tile_pts;
+    const uint32_t n_sub = (unit_pts + kTilePts - 1) / kTilePts;
+
+    // ---- count phase: sub-tiles are evaluated as their bulk copies land ----
+    for (uint32_t j = 0; j < n_sub; ++j) {
+      mbar_wait(&full_bar[j], (parity >> j) & 1u);
+      parity ^= 1u << j;
+      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
+      SmemSrc<R> src{dsm + (size_t)j * kSubBytes};
+      select_count_sub(P, S, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j]);
+    }
+    __syncthreads();
+    const uint32_t total = select_unit_total(&sel, n_sub);
+    if (warp_id() == 0) {
+      if (tid == 0) {
+        take_ticket();  // before the look-back: stages this unit does not use can start loading now
+        for (uint32_t j = n_sub; j < (uint32_t)G; ++j) issue(j);
+      }
+      __syncwarp();
+      select_publish(P, S, L, tile, total, &sel);
+    }
+    __syncthreads();
+
+    // ---- emit phase: each stage is refilled with the next unit's sub-tile as soon as it is drained ----
+    unsigned long long run = sel.out_rec;
+    for (uint32_t j = 0; j < n_sub; ++j) {
+      if (total) {
+        const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
+        SmemSrc<R> src{dsm + (size_t)j * kSubBytes};
+        run += select_emit_sub(P, S, L, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j], run, &sel);
+      }
+      // select_emit_sub ends with a barrier whenever it read the stage; when it returned early (no match in
+      // the sub-tile) the count phase barrier is the last reader of stage j
+      if (tid == 0) issue(j);
     }
   }
 }
@@ -908,9 +1103,31 @@ __global__ void k_grid_import(GridDev g, const Candidate* in, uint64_t n) {
 // ------------------------------------------------------------------------------------------------
 static int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 
+// ring depth of the scan kernels: enough stages for >= ~48 KB in flight per CTA
+template <int R>
+struct ScanStages {
+  static constexpr int value = R <= 12 ? 8 : (R <= 20 ? 6 : 4);
+};
+// group size (= ring depth) of the select kernels: ~50-70 KB ring, two CTAs per SM
+template <int R>
+struct SelectGroup {
+  static constexpr int value = R <= 12 ? 8 : (R <= 20 ? 6 : (R <= 28 ? 5 : 4));
+};
+
+static int persistent_grid(const void* kfn, size_t smem, int sm_count, uint64_t n_tiles, int max_per_sm, unsigned* grid_out) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBlock, smem) != cudaSuccess) return -1;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
+  uint64_t grid = (uint64_t)sm_count * (uint64_t)per_sm;  // persistent: every CTA resident at once
+  if (grid > n_tiles) grid = n_tiles;
+  *grid_out = (unsigned)grid;
+  return 0;
+}
+
 template <int R, int MODE>
 static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
-  constexpr int STAGES = 4;
+  constexpr int STAGES = ScanStages<R>::value;
   constexpr size_t smem = (size_t)STAGES * kTilePts * R;
   static bool configured = false;
   auto kfn = k_scan_staged<R, MODE, STAGES>;
@@ -918,14 +1135,27 @@ static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
   }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBlock, smem) != cudaSuccess) return -1;
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
-  uint64_t grid = (uint64_t)sm_count * (uint64_t)per_sm;  // persistent: every CTA resident at once
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  unsigned grid = 0;
+  if (persistent_grid((const void*)kfn, smem, sm_count, p.n_tiles, 4, &grid) != 0) return -1;
   if (grid == 0) return 0;
-  kfn<<<(unsigned)grid, kBlock, smem, st>>>(p);
+  kfn<<<grid, kBlock, smem, st>>>(p);
+  return check_launch();
+}
+
+template <int R>
+static int launch_select_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
+  constexpr int G = SelectGroup<R>::value;
+  constexpr size_t smem = (size_t)G * kTilePts * R;
+  static bool configured = false;
+  auto kfn = k_select_staged<R, G>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  unsigned grid = 0;
+  if (persistent_grid((const void*)kfn, smem, sm_count, p.n_tiles, 3, &grid) != 0) return -1;
+  if (grid == 0) return 0;
+  kfn<<<grid, kBlock, smem, st>>>(p);
   return check_launch();
 }
 
@@ -941,21 +1171,51 @@ static int launch_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaSt
   }
 }
 
+static int launch_select_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
+  switch (R) {
+    case 12: return launch_select_staged_t<12>(p, sm_count, st);
+    case 20: return launch_select_staged_t<20>(p, sm_count, st);
+    case 26: return launch_select_staged_t<26>(p, sm_count, st);
+    case 28: return launch_select_staged_t<28>(p, sm_count, st);
+    case 34: return launch_select_staged_t<34>(p, sm_count, st);
+    default: return 1;
+  }
+}
+
 template <int MODE>
 static int launch_direct_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   auto kfn = k_scan_direct<MODE>;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBlock, 0) != cudaSuccess) return -1;
-  if (per_sm < 1) per_sm = 1;
-  // look-back needs every CTA that holds a ticket to be resident: never launch more than fit at once
-  uint64_t grid = (uint64_t)sm_count * (uint64_t)per_sm;
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  unsigned grid = 0;
+  if (persistent_grid((const void*)kfn, 0, sm_count, p.n_tiles, 8, &grid) != 0) return -1;
   if (grid == 0) return 0;
-  kfn<<<(unsigned)grid, kBlock, 0, st>>>(p);
+  kfn<<<grid, kBlock, 0, st>>>(p);
+  return check_launch();
+}
+
+static int launch_select_direct(const ScanParams& p, int sm_count, cudaStream_t st) {
+  unsigned grid = 0;
+  if (persistent_grid((const void*)k_select_direct, 0, sm_count, p.n_tiles, 8, &grid) != 0) return -1;
+  if (grid == 0) return 0;
+  k_select_direct<<<grid, kBlock, 0, st>>>(p);
   return check_launch();
 }
 
 bool staged_supports(uint32_t R) { return R == 12 || R == 20 || R == 26 || R == 28 || R == 34; }
+
+// records per scheduling unit ("tile") for a launch: 512 for count / grid, a whole group for select
+uint32_t tile_points(int variant, int mode, uint32_t R) {
+  if (mode != MODE_SELECT) return kTilePts;
+  if (variant == 2 && staged_supports(R)) {
+    switch (R) {
+      case 12: return kTilePts * SelectGroup<12>::value;
+      case 20: return kTilePts * SelectGroup<20>::value;
+      case 26: return kTilePts * SelectGroup<26>::value;
+      case 28: return kTilePts * SelectGroup<28>::value;
+      default: return kTilePts * SelectGroup<34>::value;
+    }
+  }
+  return kTilePts * kMaxGroup;
+}
 
 // variant: 1 = direct, 2 = staged (needs uniform_record_len supported); returns 0 ok, <0 CUDA error
 int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int sm_count, void* stream) {
@@ -963,12 +1223,12 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
   if (variant == 2 && staged_supports(uniform_record_len)) {
     int rc = 1;
     if (mode == MODE_COUNT) rc = launch_staged_r<MODE_COUNT>(p, uniform_record_len, sm_count, st);
-    if (mode == MODE_SELECT) rc = launch_staged_r<MODE_SELECT>(p, uniform_record_len, sm_count, st);
+    if (mode == MODE_SELECT) rc = launch_select_staged_r(p, uniform_record_len, sm_count, st);
     if (mode == MODE_GRID) rc = launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
     if (rc <= 0) return rc;
   }
   if (mode == MODE_COUNT) return launch_direct_t<MODE_COUNT>(p, sm_count, st);
-  if (mode == MODE_SELECT) return launch_direct_t<MODE_SELECT>(p, sm_count, st);
+  if (mode == MODE_SELECT) return launch_select_direct(p, sm_count, st);
   return launch_direct_t<MODE_GRID>(p, sm_count, st);
 }
 

@@ -86,7 +86,7 @@ struct ScanParams {
   uint32_t n_segs;
   uint32_t query_kind;  // pcq_query_kind
   uint32_t cls;         // class byte of a class query
-  uint32_t pad_;
+  uint32_t tile_pts;    // records per scheduling unit: kTilePts, or a whole look-back group for MODE_SELECT
   uint64_t n_tiles;
   const LaneDev* lanes;
   unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
@@ -95,6 +95,7 @@ struct ScanParams {
 
 // launch wrappers implemented in kernels.cu (stream is a cudaStream_t); 0 = ok, < 0 = CUDA error
 bool staged_supports(uint32_t record_len);
+uint32_t tile_points(int variant, int mode, uint32_t record_len);
 int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int sm_count, void* stream);
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
 int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count, int sm_count,

@@ -52,6 +52,9 @@ def main():
             ts.append(e0.elapsed_time(e1))
         return statistics.median(ts)
 
+    if args.only == "configs":
+        run_configs(pcq, ctx, stream, timed, peak, args)
+        return
     cases = [("las", 0), ("las", 1), ("las", 2), ("las", 3), ("last", 1), ("last", 3)]
     for ext, fmt in cases:
         layout = B.LAYOUT_LAS if ext == "las" else B.LAYOUT_LAST
@@ -142,6 +145,109 @@ def main():
         df.release()
         del buf
         torch.cuda.empty_cache()
+
+
+def run_configs(pcq, ctx, stream, timed, peak, args):
+    """BASELINE.json configs[2] (C3, ca13-shape LAST class queries with compacted output) and configs[3]
+    (C4, navvis-shape dense LAS, bounds + max-density) at their full per-GPU sizes."""
+    import time
+
+    import torch
+
+    S, B = pcq.synth, pcq.binding
+    impl = pcq.SearchImplementation.Optimized
+
+    def out(d):
+        print(json.dumps(d), flush=True)
+
+    # ---- C4: one navvis-shape file, 56.2 M points, format 3, S/L/XL + density 0.1 ----
+    for fma in (False, True):
+        sp = S.navvis_spec(n_points=56_200_000, fma_sensitive=fma)
+        buf = torch.empty(sp.n_points * sp.record_len + 256, dtype=torch.uint8, device="cuda:0")
+        mm, desc = S.device_points(ctx, sp, buf.data_ptr())
+        df = pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf)
+        for name, (qmin, qmax) in (("S", S.NAVVIS_S), ("L", S.NAVVIS_L), ("XL", S.NAVVIS_XL)):
+            s = pcq.BoundsSearcher(qmin, qmax)
+            cc = pcq.CountCollector(ctx)
+            ms_count = timed(lambda: s.search_files([df], impl, [cc]))
+            cc.reset()
+            s.search_files([df], impl, [cc])
+            matches = cc.point_count()
+            g = pcq.GridSampledCollector(qmin, qmax, S.NAVVIS_DENSITY, ctx=ctx)
+
+            def run():
+                g.reset()
+                s.search_files([df], impl, [g])
+
+            ms_grid = timed(run, reps=5)
+            run()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            cells = g.point_count()
+            fin_ms = (time.perf_counter() - t0) * 1e3
+            bc = pcq.BufferCollector(ctx)
+
+            def runb():
+                bc.reset()
+                s.search_files([df], impl, [bc])
+
+            ms_sel = timed(runb, reps=5)
+            nb = sp.n_points * sp.record_len
+            out({"config": "C4 navvis", "fma_sensitive_header": fma, "box": name, "points": sp.n_points, "matches": matches, "cells": cells,
+                 "count_ms": ms_count, "count_gbs": nb / ms_count / 1e6, "select_ms": ms_sel,
+                 "select_gbs": (nb + 31 * matches) / ms_sel / 1e6, "density_insert_ms": ms_grid,
+                 "density_insert_gbs": (nb + 8 * matches) / ms_grid / 1e6, "density_finalize_ms_host_timed": fin_ms,
+                 "density_total_gpoints_per_s": sp.n_points / (ms_grid + fin_ms) / 1e6, "peak_gbs": peak})
+            g.close()
+            bc.close()
+        df.release()
+        del buf
+        torch.cuda.empty_cache()
+
+    # ---- C3: ca13-shape LAST, 64 files x 40.75 M points (only the three columns the path reads are resident) ----
+    specs = S.ca13_specs()
+    dfs, keep = [], []
+    for sp in specs:
+        # generate the full transposed record block, then keep only position / class columns (19 of 28 bytes are never read)
+        buf = torch.empty(sp.n_points * sp.record_len + 256, dtype=torch.uint8, device="cuda:0")
+        mm, desc = S.device_points(ctx, sp, buf.data_ptr())
+        host_needed = None
+        dfs.append(pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf))
+        keep.append(buf)
+    total = sum(sp.n_points for sp in specs)
+    for klass in (2, 6, 19):
+        s = pcq.ClassSearcher(klass)
+        cols = [pcq.CountCollector(ctx) for _ in dfs]
+        ms_count = timed(lambda: s.search_files(dfs, impl, cols))
+        for c in cols:
+            c.reset()
+        s.search_files(dfs, impl, cols)
+        matches = sum(c.point_count() for c in cols)
+        bcols = [pcq.BufferCollector(ctx) for _ in dfs]
+
+        def runb():
+            for c in bcols:
+                c.reset()
+            s.search_files(dfs, impl, bcols)
+
+        ms_sel = timed(runb, reps=5)
+        assert sum(c.point_count() for c in bcols) == matches
+        out({"config": "C3 ca13 LAST", "class": klass, "points": total, "matches": matches, "count_ms": ms_count,
+             "count_gbs": total / ms_count / 1e6, "count_gpoints_per_s": total / ms_count / 1e6, "select_ms": ms_sel,
+             "select_gbs": (total + matches * (12 + 31)) / ms_sel / 1e6, "select_gpoints_per_s": total / ms_sel / 1e6, "peak_gbs": peak})
+        for c in bcols:
+            c.close()
+    for (name, box) in (("S", S.CA13_S), ("L", S.CA13_L), ("XL", S.CA13_XL)):
+        s = pcq.BoundsSearcher(*box)
+        cols = [pcq.CountCollector(ctx) for _ in dfs]
+        ms_count = timed(lambda: s.search_files(dfs, impl, cols))
+        for c in cols:
+            c.reset()
+        s.search_files(dfs, impl, cols)
+        per = [c.point_count() for c in cols]
+        scanned = sum(sp.n_points for sp, df in zip(specs, dfs))  # upper bound; tiles skipped by the header test cost nothing
+        out({"config": "C3 ca13 LAST", "box": name, "points": total, "matches": sum(per), "count_ms": ms_count,
+             "count_gpoints_per_s_dataset": total / ms_count / 1e6, "peak_gbs": peak})
 
 
 if __name__ == "__main__":
