@@ -247,6 +247,7 @@ void fill_segment(Segment* s, const pcq_file_desc& d, const uint8_t* rec, const 
     s->cls_off = 0;
     s->rgb_off = -1;
     s->align = field_alignment(rec, 12);
+    s->rgb_align2 = (reinterpret_cast<uintptr_t>(rgb) & 1u) == 0 ? 1 : 0;
   }
 }
 
@@ -443,7 +444,9 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
   uint32_t R = segs[0].record_len;
   bool staged_ok = staged_supports(R);
   bool all_last = true;
+  int min_align = 4;
   for (const Segment& s : segs) {
+    min_align = std::min<int>(min_align, s.align);
     if (s.record_len != R) staged_ok = false;
     if ((reinterpret_cast<uintptr_t>(s.rec) & 15u) != 0) staged_ok = false;
     if (s.layout == PCQ_LAYOUT_LAST && q->kind == PCQ_QUERY_CLASS) staged_ok = false;
@@ -512,6 +515,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     P.tile_pts = tile_pts;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
     if (mode == MODE_SELECT) {
+      if (const char* e = std::getenv("PCQ_SELECT_DEBUG")) P.debug = (uint32_t)std::atoi(e);
       RC(ensure_tile_state(ctx, n_tiles));
       P.ticket = ctx->tile_state;
       P.tile_state = ctx->tile_state + 1;
@@ -521,7 +525,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     if (mode == MODE_COUNT && q->kind == PCQ_QUERY_CLASS && all_last) {
       lrc = launch_class_count_soa(P, ctx->sm_count, ctx->stream);
     } else {
-      lrc = launch_scan(variant, mode, P, R, ctx->sm_count, ctx->stream);
+      lrc = launch_scan(variant, mode, P, R, min_align, ctx->sm_count, ctx->stream);
     }
     if (lrc != 0) return fail(PCQ_ERR_CUDA, "scan kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->launches++;

@@ -237,27 +237,38 @@ __device__ __forceinline__ void point_words(const Segment& S, const Hit& h, cons
   w[7] = (rgb[2] & 0xFFFFu) | ((h.cls & 0xFFu) << 16);
 }
 
-// Store a 31-byte record at an arbitrarily aligned shared-memory address: 7 word stores + 3 byte
-// stores instead of 31 byte stores.
+// Store a 31-byte record at an arbitrarily aligned shared-memory address as 7 word stores, one 16-bit
+// store and one byte store (w[j] = record bytes 4j .. 4j+3, top byte of w[7] zero).
 __device__ __forceinline__ void sts_point31(uint8_t* dst, const uint32_t w[8]) {
   const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
-  if (o == 0) {
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  uint8_t* a = dst - o;  // word aligned; record byte i lives at a[o + i]
+  uint32_t* d = reinterpret_cast<uint32_t*>(a);
+  switch (o) {
+    case 0:
 #pragma unroll
-    for (int j = 0; j < 7; ++j) d[j] = w[j];
-    dst[28] = (uint8_t)w[7];
-    dst[29] = (uint8_t)(w[7] >> 8);
-    dst[30] = (uint8_t)(w[7] >> 16);
-    return;
+      for (int j = 0; j < 7; ++j) d[j] = w[j];
+      *reinterpret_cast<uint16_t*>(a + 28) = (uint16_t)w[7];
+      a[30] = (uint8_t)(w[7] >> 16);
+      break;
+    case 1:
+      a[1] = (uint8_t)w[0];
+      *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)(w[0] >> 8);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 24);
+      break;
+    case 2:
+      *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)w[0];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 16);
+      a[32] = (uint8_t)(w[7] >> 16);
+      break;
+    default:
+      a[3] = (uint8_t)w[0];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 8);
+      *reinterpret_cast<uint16_t*>(a + 32) = (uint16_t)(w[7] >> 8);
+      break;
   }
-  const uint32_t head = 4u - o;  // bytes before the first aligned word
-  for (uint32_t b = 0; b < head; ++b) dst[b] = (uint8_t)(w[0] >> (8u * b));
-  uint32_t* d = reinterpret_cast<uint32_t*>(dst + head);
-  const uint32_t sh = 8u * head;
-#pragma unroll
-  for (int j = 0; j < 7; ++j) d[j] = __funnelshift_r(w[j], w[j + 1], sh);  // stream bytes 4j+head .. +3
-  // bytes written so far: head + 28; remaining = 3 - head
-  for (uint32_t b = head + 28u; b < 31u; ++b) dst[b] = (uint8_t)(w[7] >> (8u * (b & 3u)));  // b>>2 == 7
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,9 +289,12 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Executed by all 32 lanes of warp 0.  Returns the number of matches in units
+// Executed by all 32 lanes of one warp.  Returns the number of matches in units
 // [lane_first_tile, tile) — the exclusive prefix of `tile` within its lane.  Every lane inspects
-// four descriptors per round trip (window of 128 units), closest units in the lowest lanes.
+// kLookback descriptors per round trip (window of 32 * kLookback units); each load instruction of the
+// warp covers 32 consecutive descriptors (256 bytes).
+constexpr int kLookback = 8;
+
 __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* state, uint64_t tile,
                                                                  uint64_t lane_first_tile) {
   unsigned long long excl = 0;
@@ -288,34 +302,40 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
   const long long lo = (long long)lane_first_tile;
   const uint32_t ln = lane_id();
   while (hi >= lo) {
-    unsigned long long sv[4];
+    unsigned long long sv[kLookback];  // sv[k] = descriptor at distance 32 k + lane below `hi` (coalesced)
     bool pending;
     do {
       pending = false;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long t = hi - (long long)(4u * ln + (uint32_t)k);
+      for (int k = 0; k < kLookback; ++k) {
+        const long long t = hi - (long long)(32u * (uint32_t)k + ln);
         sv[k] = t >= lo ? ld_state(state + t) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
         pending |= (sv[k] >> kStatusShift) == 0ull;
       }
     } while (__any_sync(0xffffffffu, pending));
-    int kf = 4;  // first (closest) descriptor of this lane that already carries an inclusive prefix
+    // closest descriptor that already carries an inclusive prefix: row kf, lane lf
+    int kf = kLookback;
+    uint32_t lf = 32u;
 #pragma unroll
-    for (int k = 3; k >= 0; --k)
-      if ((sv[k] >> kStatusShift) == kStPrefix) kf = k;
-    const uint32_t pm = __ballot_sync(0xffffffffu, kf < 4);
-    const uint32_t first = pm ? (uint32_t)__ffs((int)pm) - 1u : 32u;
+    for (int k = kLookback - 1; k >= 0; --k) {
+      const uint32_t pmk = __ballot_sync(0xffffffffu, (sv[k] >> kStatusShift) == kStPrefix);
+      if (pmk) {
+        kf = k;
+        lf = (uint32_t)__ffs((int)pmk) - 1u;
+      }
+    }
+    const uint32_t pm = kf < kLookback ? 1u : 0u;
     unsigned long long v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool take = ln < first || (ln == first && k <= kf);
+    for (int k = 0; k < kLookback; ++k) {
+      const bool take = k < kf || (k == kf && ln <= lf);
       if (take) v += sv[k] & kValueMask;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     excl += v;
     if (pm != 0u) break;
-    hi -= 128;
+    hi -= 32 * kLookback;
   }
   return excl;
 }
@@ -638,279 +658,369 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 
 // ------------------------------------------------------------------------------------------------
 // MODE_SELECT — BufferCollector::collect_one in scan order (collect_points.rs:29-31): single-pass
-// stable stream compaction.
+// stable stream compaction with a decoupled look-back prefix.
 //
-// The unit of the decoupled look-back is a GROUP of up to kMaxGroup sub-tiles (512 records each)
-// handled by one CTA: (1) count phase — evaluate every sub-tile, keep per-warp match counts in
-// shared memory; (2) publish the unit's aggregate, take the ticket of the NEXT unit, look back
-// over earlier units for the exclusive prefix; (3) emit phase — re-evaluate each sub-tile, compose
-// its matching 31-byte records contiguously in shared memory and flush them with 16-byte stores.
-// At 6.5 TB/s a 512-record tile lasts ~2 ns, far shorter than one L2 round trip; 2-4 K-record units
-// keep the number of unresolved predecessors within one or two 128-wide look-back windows.
+// A *unit* is kSelUnitPts consecutive records of one segment.  A CTA is kSelWarps consumer warps plus
+// one look-back warp; there is no CTA-wide barrier, the warps meet on mbarriers only:
+//   look-back warp   takes the unit tickets (two units ahead), copies the unit's Segment into shared
+//                    memory, and — once the consumers have counted a unit — publishes its aggregate,
+//                    resolves the exclusive prefix over earlier units (256 descriptors per round trip)
+//                    and hands the unit's first output slot to the consumers.
+//   consumer warp w  owns records [256 w, 256 w + 256) of every unit, as 8 rows of 32 consecutive
+//                    records (8 independent loads per lane in flight).  Per unit: evaluate the
+//                    predicate, keep the 8 ballot masks, post the warp count; then emit the PREVIOUS
+//                    unit (whose look-back ran while this unit's loads were in flight): matching lanes
+//                    re-read their record (L2), compose the 31-byte Point in a warp-private staging
+//                    buffer that has the 16-byte phase of its destination, and the warp flushes it
+//                    with aligned 16-byte stores (loose bytes at both ends as byte stores).
 // Tickets (not blockIdx) order the units, so a unit only ever waits for units held by running CTAs.
+// At 6.5 TB/s a 2048-record unit lasts 4-9 ns while one L2 round trip is ~500 ns: the 256-wide
+// look-back window is what keeps the chain of unresolved predecessors from limiting throughput
+// (bound = 256 units * unit bytes / round trip, > 12 TB/s for every record length).
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxGroup = 8;
+constexpr int kSelWarps = 8;
+constexpr int kSelRows = 8;
+constexpr int kSelWarpPts = 32 * kSelRows;
+constexpr int kSelUnitPts = kSelWarps * kSelWarpPts;  // 2048
+constexpr int kSelThreads = (kSelWarps + 2) * 32;  // + look-back warp + dispatcher warp
+constexpr int kSelBufs = 6;        // unit descriptors per CTA: n-2 (emit) .. n+1 (loads) + two ticketed ahead
+constexpr int kSelStageRecs = 64;  // records composed per flush round of a warp
+constexpr int kSelStageBytes = 2048;  // 64 * 31 + 15 phase bytes, rounded up
 
-struct SelectShared {
-  uint32_t warp_cnt[kMaxGroup][kPPT][kBlock / 32];
-  unsigned long long out_rec;   // lane.out_base + exclusive prefix of the current unit
-  unsigned long long cur_tile;  // direct kernel: ticket broadcast
-  alignas(16) uint8_t stage[kTilePts * 31 + 32];
+struct SelUnit {
+  Segment seg;
+  unsigned long long tile;      // ~0 = no more units
+  unsigned long long u0;        // first record of the unit within its segment
+  unsigned long long out_rec;   // lane.out_base + exclusive prefix (set by the look-back warp)
+  unsigned long long out_base;
+  unsigned long long out_cap;
+  uint8_t* out;
+  unsigned long long* count;
+  uint32_t npts;
+  uint32_t acc;  // consumers: sum of posted warp counts | number of posted warps << 24
+  uint32_t warp_cnt[kSelWarps];
 };
 
-template <class Src>
-__device__ __forceinline__ void select_count_sub(const ScanParams& P, const Segment& S, const Src& src, uint64_t p0,
-                                                 uint32_t npts, uint32_t (*warp_cnt)[kBlock / 32]) {
-#pragma unroll
-  for (int j = 0; j < kPPT; ++j) {
-    const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
-    Hit h;
-    bool m = false;
-    if (i < npts) m = src.template eval<false>(S, P.query_kind, P.cls, p0 + i, i, h);
-    const uint32_t bal = __ballot_sync(0xffffffffu, m);
-    if (lane_id() == 0) warp_cnt[j][warp_id()] = (uint32_t)__popc(bal);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// loads of little-endian fields whose alignment AL (4, 2 or 1) is a compile-time constant
+template <int AL>
+__device__ __forceinline__ int32_t ldg_i32_a(const uint8_t* p) {
+  if constexpr (AL == 4) {
+    return __ldg(reinterpret_cast<const int32_t*>(p));
+  } else if constexpr (AL == 2) {
+    const uint32_t a = __ldg(reinterpret_cast<const uint16_t*>(p));
+    const uint32_t b = __ldg(reinterpret_cast<const uint16_t*>(p + 2));
+    return (int32_t)(a | (b << 16));
+  } else {
+    const uint32_t b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+    return (int32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+  }
+}
+template <int AL>
+__device__ __forceinline__ uint32_t ldg_u16_a(const uint8_t* p) {
+  if constexpr (AL >= 2) {
+    return __ldg(reinterpret_cast<const uint16_t*>(p));
+  } else {
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8);
   }
 }
 
-// all sub-tile counts of the unit are in shared memory (and synchronised) when this runs;
-// returns the number of matches of the sub-tile
-template <class Src>
-__device__ __forceinline__ uint32_t select_emit_sub(const ScanParams& P, const Segment& S, const LaneDev& L, const Src& src,
-                                                    uint64_t p0, uint32_t npts, const uint32_t (*warp_cnt)[kBlock / 32],
-                                                    unsigned long long out_rec, SelectShared* sel) {
-  const uint32_t tid = threadIdx.x;
-  Hit h[kPPT];
-  bool m[kPPT];
-  uint32_t my_off[kPPT];
-  uint32_t total = 0;
-#pragma unroll
-  for (int j = 0; j < kPPT; ++j) {
-    const uint32_t i = (uint32_t)j * kBlock + tid;
-    m[j] = false;
-    if (i < npts) m[j] = src.template eval<true>(S, P.query_kind, P.cls, p0 + i, i, h[j]);
-    const uint32_t bal = __ballot_sync(0xffffffffu, m[j]);
-    my_off[j] = 0;
-#pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) {
-      const uint32_t c = warp_cnt[j][w];
-      if (w == (int)warp_id()) my_off[j] = total + (uint32_t)__popc(bal & ((1u << lane_id()) - 1u));
-      total += c;
-    }
-  }
-  if (total == 0) {  // uniform: nothing to write for this sub-tile
-    __syncthreads();  // ... but every thread must be done reading the stage before the caller refills it
-    return 0;
-  }
-  const unsigned long long gb0 = out_rec * 31ull;     // first output byte of this sub-tile
-  const uint32_t so = (uint32_t)(gb0 & 15ull);        // keep global and shared 16-byte phases equal
-#pragma unroll
-  for (int j = 0; j < kPPT; ++j) {
-    if (m[j]) {
-      const uint32_t i = (uint32_t)j * kBlock + tid;
-      uint32_t rgb[3];
-      src.colour(S, p0 + i, i, rgb);
-      uint32_t w[8];
-      point_words(S, h[j], rgb, w);
-      sts_point31(sel->stage + so + my_off[j] * 31u, w);
-    }
-  }
-  __syncthreads();
-  // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
-  const unsigned long long room = out_rec < L.out_cap ? L.out_cap - out_rec : 0ull;
-  const uint32_t n_ok = room < (unsigned long long)total ? (uint32_t)room : total;
-  const uint32_t nb = n_ok * 31u;
-  if (nb) {
-    uint8_t* gout = L.out + gb0;  // byte address of stage[so]
-    uint32_t head = (16u - so) & 15u;
-    if (head > nb) head = nb;
-    const uint32_t nvec = (nb - head) >> 4;
-    const uint32_t tail0 = head + (nvec << 4);
-    if (tid < head) gout[tid] = sel->stage[so + tid];
-    const uint4* svec = reinterpret_cast<const uint4*>(sel->stage + so + head);
-    uint4* gvec = reinterpret_cast<uint4*>(gout + head);
-    for (uint32_t k = tid; k < nvec; k += kBlock) gvec[k] = svec[k];
-    if (tid < nb - tail0) gout[tail0 + tid] = sel->stage[so + tail0 + tid];
-  }
-  __syncthreads();  // the staging buffer is reused by the next sub-tile
-  return total;
-}
+struct RawPoint {
+  int32_t x, y, z;
+  uint32_t cls, r, g, b;
+};
 
-// sum of all sub-tile counts of a unit (uniform across the CTA)
-__device__ __forceinline__ uint32_t select_unit_total(const SelectShared* sel, uint32_t n_sub) {
-  uint32_t total = 0;
-  for (uint32_t j = 0; j < n_sub; ++j)
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k)
-#pragma unroll
-      for (int w = 0; w < kBlock / 32; ++w) total += sel->warp_cnt[j][k][w];
-  return total;
-}
-
-// warp 0: publish the unit's aggregate / prefix, resolve its exclusive prefix, bump the lane's count
-__device__ __forceinline__ void select_publish(const ScanParams& P, const Segment& S, const LaneDev& L, uint64_t tile,
-                                               uint32_t total, SelectShared* sel) {
-  unsigned long long excl = 0;
-  const bool first = tile == S.lane_first_tile;
-  if (!first) {
-    if (lane_id() == 0) st_state(P.tile_state + tile, (kStAgg << kStatusShift) | (unsigned long long)total);
-    excl = lookback_exclusive(P.tile_state, tile, S.lane_first_tile);
-  }
-  if (lane_id() == 0) {
-    st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
-    sel->out_rec = L.out_base + excl;
-    if (total) atomicAdd(L.count, (unsigned long long)total);
-  }
-}
-
-__global__ void __launch_bounds__(kBlock) k_select_direct(ScanParams P) {
-  __shared__ Segment sseg;
-  __shared__ SelectShared sel;
-  uint32_t seg_i = 0xFFFFFFFFu, seg_cursor = 0;
-  DirectSrc src;
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) sel.cur_tile = atomicAdd(P.ticket, 1ull);
-    __syncthreads();
-    const uint64_t tile = sel.cur_tile;
-    if (tile >= P.n_tiles) break;
-    while (seg_cursor + 1 < P.n_segs && tile >= P.segs[seg_cursor + 1].first_tile) ++seg_cursor;
-    if (seg_cursor != seg_i) {
-      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_cursor);
-      uint32_t* dstw = reinterpret_cast<uint32_t*>(&sseg);
-      for (uint32_t k = threadIdx.x; k < sizeof(Segment) / 4; k += kBlock) dstw[k] = srcw[k];
-      seg_i = seg_cursor;
-      __syncthreads();
+// all fields of two records at once (14 independent loads per lane in flight)
+template <int AL>
+__device__ __forceinline__ void select_fetch2(const Segment& S, uint64_t i0, uint64_t i1, RawPoint& a, RawPoint& b) {
+  const uint8_t* p0 = S.rec + i0 * (uint64_t)S.record_len;  // LAST: record_len == 12 (positions column)
+  const uint8_t* p1 = S.rec + i1 * (uint64_t)S.record_len;
+  a.x = ldg_i32_a<AL>(p0);
+  a.y = ldg_i32_a<AL>(p0 + 4);
+  a.z = ldg_i32_a<AL>(p0 + 8);
+  b.x = ldg_i32_a<AL>(p1);
+  b.y = ldg_i32_a<AL>(p1 + 4);
+  b.z = ldg_i32_a<AL>(p1 + 8);
+  a.r = a.g = a.b = b.r = b.g = b.b = 0u;  // Vector3::new(0, 0, 0), las.rs:134
+  if (S.layout == PCQ_LAYOUT_LAS) {
+    a.cls = __ldg(p0 + S.cls_off);
+    b.cls = __ldg(p1 + S.cls_off);
+    if (S.rgb_off >= 0) {
+      const uint8_t* c0 = p0 + (uint32_t)S.rgb_off;  // 20 / 28: as aligned as the record itself (up to 2)
+      const uint8_t* c1 = p1 + (uint32_t)S.rgb_off;
+      a.r = ldg_u16_a<AL>(c0);
+      a.g = ldg_u16_a<AL>(c0 + 2);
+      a.b = ldg_u16_a<AL>(c0 + 4);
+      b.r = ldg_u16_a<AL>(c1);
+      b.g = ldg_u16_a<AL>(c1 + 2);
+      b.b = ldg_u16_a<AL>(c1 + 4);
     }
-    const Segment& S = sseg;
-    const LaneDev& L = P.lanes[S.lane];
-    const uint64_t u0 = (tile - S.first_tile) * (uint64_t)P.tile_pts;
-    const uint64_t rem = S.n_points - u0;
-    const uint32_t unit_pts = rem < (uint64_t)P.tile_pts ? (uint32_t)rem : P.tile_pts;
-    const uint32_t n_sub = (unit_pts + kTilePts - 1) / kTilePts;
-    for (uint32_t j = 0; j < n_sub; ++j) {
-      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
-      select_count_sub(P, S, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j]);
-    }
-    __syncthreads();
-    const uint32_t total = select_unit_total(&sel, n_sub);
-    if (warp_id() == 0) select_publish(P, S, L, tile, total, &sel);
-    __syncthreads();
-    unsigned long long run = sel.out_rec;
-    if (total == 0) continue;
-    for (uint32_t j = 0; j < n_sub; ++j) {
-      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
-      run += select_emit_sub(P, S, L, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j], run, &sel);
+  } else {
+    a.cls = __ldg(S.cls + i0);
+    b.cls = __ldg(S.cls + i1);
+    if (S.rgb != nullptr) {
+      const uint8_t* c0 = S.rgb + i0 * 6ull;
+      const uint8_t* c1 = S.rgb + i1 * 6ull;
+      if (S.rgb_align2) {
+        a.r = ldg_u16_a<2>(c0);
+        a.g = ldg_u16_a<2>(c0 + 2);
+        a.b = ldg_u16_a<2>(c0 + 4);
+        b.r = ldg_u16_a<2>(c1);
+        b.g = ldg_u16_a<2>(c1 + 2);
+        b.b = ldg_u16_a<2>(c1 + 4);
+      } else {
+        a.r = ldg_u16_a<1>(c0);
+        a.g = ldg_u16_a<1>(c0 + 2);
+        a.b = ldg_u16_a<1>(c0 + 4);
+        b.r = ldg_u16_a<1>(c1);
+        b.g = ldg_u16_a<1>(c1 + 2);
+        b.b = ldg_u16_a<1>(c1 + 4);
+      }
     }
   }
 }
 
-// staged variant: the G sub-tiles of a unit are the G stages of the bulk-copy ring
-template <int R, int G>
-__global__ void __launch_bounds__(kBlock) k_select_staged(ScanParams P) {
-  static_assert(G <= kMaxGroup, "group larger than the count table");
-  constexpr uint32_t kSubBytes = (uint32_t)kTilePts * (uint32_t)R;
-  extern __shared__ __align__(128) uint8_t dsm[];  // G * kSubBytes
-  __shared__ __align__(8) uint64_t full_bar[G];
-  __shared__ Segment sseg;
-  __shared__ SelectShared sel;
-  struct Next {
-    unsigned long long tile;  // ~0 = no more units
-    const uint8_t* src;       // first record of the unit
-    uint32_t npts;
-    uint32_t seg;
-  };
-  __shared__ Next nxt;
+__device__ __forceinline__ void select_compose(const Segment& S, const RawPoint& q, uint8_t* dst) {
+  Hit h;
+  h.x = q.x;
+  h.y = q.y;
+  h.z = q.z;
+  h.cls = q.cls;
+  const uint32_t rgb[3] = {q.r, q.g, q.b};
+  uint32_t wd[8];
+  point_words(S, h, rgb, wd);
+  sts_point31(dst, wd);
+}
 
-  const uint32_t tid = threadIdx.x;
-  uint32_t prod_seg = 0;  // thread 0 only
-
-  auto take_ticket = [&]() {
-    const unsigned long long tile = atomicAdd(P.ticket, 1ull);
-    if (tile >= P.n_tiles) {
-      nxt.tile = ~0ull;
-      return;
-    }
-    while (prod_seg + 1 < P.n_segs && tile >= P.segs[prod_seg + 1].first_tile) ++prod_seg;
-    const Segment* sg = P.segs + prod_seg;
-    const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)P.tile_pts;
-    const uint64_t rem = sg->n_points - u0;
-    nxt.tile = tile;
-    nxt.src = sg->rec + u0 * (uint64_t)R;
-    nxt.npts = rem < (uint64_t)P.tile_pts ? (uint32_t)rem : P.tile_pts;
-    nxt.seg = prod_seg;
-  };
-  // load sub-tile j of the NEXT unit into stage j (thread 0)
-  auto issue = [&](uint32_t j) {
-    if (nxt.tile == ~0ull) return;
-    const uint32_t off = j * (uint32_t)kTilePts;
-    if (off >= nxt.npts) return;
-    const uint32_t n = min((uint32_t)kTilePts, nxt.npts - off);
-    const uint32_t bytes = (n * (uint32_t)R + 15u) & ~15u;
-    mbar_arrive_expect_tx(&full_bar[j], bytes);
-    bulk_copy_g2s(dsm + (size_t)j * kSubBytes, nxt.src + (uint64_t)off * R, bytes, &full_bar[j]);
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int j = 0; j < G; ++j) mbar_init(&full_bar[j], 1u);
-    mbar_fence_init();
-    take_ticket();
+// Emit the matches of consumer warp `w` in unit U (all 32 lanes call it).  `list` holds the unit-local
+// record index of the warp's r-th match.  Dense: lane l composes matches l and l + 32 of each round of 64.
+template <int AL>
+__device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_t* list, uint8_t* stage) {
+  const uint32_t w = warp_id(), ln = lane_id();
+  const uint32_t mine = U.warp_cnt[w];
+  if (mine == 0) return;
+  uint32_t before = 0;
+  for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
+  const unsigned long long out0 = U.out_rec + before;
+  const Segment& S = U.seg;
+  const uint64_t wbase = U.u0 + (uint64_t)w * kSelWarpPts;
 #pragma unroll 1
-    for (uint32_t j = 0; j < (uint32_t)G; ++j) issue(j);
+  for (uint32_t base = 0; base < mine; base += kSelStageRecs) {
+    const unsigned long long orec = out0 + base;
+    const unsigned long long g0 = orec * 31ull;      // first output byte of this round
+    const uint32_t phase = (uint32_t)(g0 & 15ull);   // keep global and shared 16-byte phases equal
+    const uint32_t n = min((uint32_t)kSelStageRecs, mine - base);
+    const uint32_t r0 = ln, r1 = ln + 32u;
+    // lanes beyond the round's records fetch the round's first record again (always a valid address)
+    const uint64_t i0 = wbase + list[base + (r0 < n ? r0 : 0u)];
+    const uint64_t i1 = wbase + list[base + (r1 < n ? r1 : 0u)];
+    RawPoint q0, q1;
+    select_fetch2<AL>(S, i0, i1, q0, q1);
+    if (r0 < n) select_compose(S, q0, stage + phase + r0 * 31u);
+    if (r1 < n) select_compose(S, q1, stage + phase + r1 * 31u);
+    __syncwarp();
+    // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
+    const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
+    const uint32_t nb = (room < (unsigned long long)n ? (uint32_t)room : n) * 31u;
+    if (nb) {
+      uint8_t* gbase = U.out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
+      const uint32_t end = phase + nb;
+      const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;  // full 16-byte chunks [c_first, c_end)
+      if (phase + ln < (c_first << 4)) gbase[phase + ln] = stage[phase + ln];
+      const uint4* sv = reinterpret_cast<const uint4*>(stage);
+      uint4* gv = reinterpret_cast<uint4*>(gbase);
+      for (uint32_t c = c_first + ln; c < c_end; c += 32u) gv[c] = sv[c];
+      const uint32_t tb = (c_end << 4) + ln;
+      if (tb < end) gbase[tb] = stage[tb];
+    }
+    __syncwarp();  // the staging buffer is reused by the next round / unit
+  }
+}
+
+template <int AL>
+__global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
+  __shared__ SelUnit unit[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_tk[kSelBufs];    // unit descriptor filled    (dispatcher -> consumers, look-back warp)
+  __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];   // all warp counts posted    (consumers -> look-back warp)
+  __shared__ __align__(8) uint64_t bar_pre[kSelBufs];   // exclusive prefix resolved (look-back warp -> consumers)
+  __shared__ __align__(8) uint64_t bar_free[kSelBufs];  // unit emitted              (consumers -> dispatcher)
+  __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
+  __shared__ uint16_t match_list[kSelWarps][3][kSelWarpPts];  // unit-local index of each warp's r-th match
+
+  const uint32_t ln = lane_id();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int b = 0; b < kSelBufs; ++b) {
+      mbar_init(&bar_tk[b], 1u);
+      mbar_init(&bar_cnt[b], (uint32_t)kSelWarps);
+      mbar_init(&bar_pre[b], 1u);
+      mbar_init(&bar_free[b], (uint32_t)kSelWarps);
+    }
+    mbar_fence_init();
   }
   __syncthreads();
 
-  uint32_t parity = 0;  // bit j: parity of the next completion of stage j
-  uint32_t seg_i = 0xFFFFFFFFu;
-  for (;;) {
-    const unsigned long long tile = nxt.tile;
-    if (tile == ~0ull) break;
-    const uint32_t unit_pts = nxt.npts;
-    const uint32_t seg_now = nxt.seg;
-    if (seg_now != seg_i) {
-      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_now);
-      uint32_t* dstw = reinterpret_cast<uint32_t*>(&sseg);
-      for (uint32_t k = tid; k < sizeof(Segment) / 4; k += kBlock) dstw[k] = srcw[k];
-      seg_i = seg_now;
-    }
-    __syncthreads();  // everyone has read nxt (thread 0 overwrites it below); sseg is complete
-    const Segment& S = sseg;
-    const LaneDev& L = P.lanes[S.lane];
-    const uint64_t u0 = (tile - S.first_tile) * (uint64_t)P.tile_pts;
-    const uint32_t n_sub = (unit_pts + kTilePts - 1) / kTilePts;
-
-    // ---- count phase: sub-tiles are evaluated as their bulk copies land ----
-    for (uint32_t j = 0; j < n_sub; ++j) {
-      mbar_wait(&full_bar[j], (parity >> j) & 1u);
-      parity ^= 1u << j;
-      const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
-      SmemSrc<R> src{dsm + (size_t)j * kSubBytes};
-      select_count_sub(P, S, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j]);
-    }
-    __syncthreads();
-    const uint32_t total = select_unit_total(&sel, n_sub);
-    if (warp_id() == 0) {
-      if (tid == 0) {
-        take_ticket();  // before the look-back: stages this unit does not use can start loading now
-        for (uint32_t j = n_sub; j < (uint32_t)G; ++j) issue(j);
+  if (warp_id() == kSelWarps + 1) {
+    // ---------------- dispatcher warp: tickets and unit descriptors, never blocked by a look-back ----------------
+    uint32_t seg_cur = 0;
+    for (uint32_t n = 0;; ++n) {
+      const uint32_t b = n % kSelBufs;
+      if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
+      unsigned long long tile = 0;
+      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      SelUnit& U = unit[b];
+      if (ln == 0) U.acc = 0u;
+      if (tile >= P.n_tiles) {
+        if (ln == 0) {
+          U.tile = ~0ull;
+          mbar_arrive(&bar_tk[b]);
+        }
+        break;
+      }
+      while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
+      const Segment* sg = P.segs + seg_cur;
+      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
+      for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+      if (ln == 0) {
+        const LaneDev* L = P.lanes + sg->lane;
+        const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)kSelUnitPts;
+        const uint64_t rem = sg->n_points - u0;
+        U.tile = tile;
+        U.u0 = u0;
+        U.npts = rem < (uint64_t)kSelUnitPts ? (uint32_t)rem : (uint32_t)kSelUnitPts;
+        U.out = L->out;
+        U.out_cap = L->out_cap;
+        U.out_base = L->out_base;
+        U.count = L->count;
       }
       __syncwarp();
-      select_publish(P, S, L, tile, total, &sel);
+      if (ln == 0) mbar_arrive(&bar_tk[b]);
     }
-    __syncthreads();
+    return;
+  }
 
-    // ---- emit phase: each stage is refilled with the next unit's sub-tile as soon as it is drained ----
-    unsigned long long run = sel.out_rec;
-    for (uint32_t j = 0; j < n_sub; ++j) {
-      if (total) {
-        const uint32_t np = min((uint32_t)kTilePts, unit_pts - j * kTilePts);
-        SmemSrc<R> src{dsm + (size_t)j * kSubBytes};
-        run += select_emit_sub(P, S, L, src, u0 + (uint64_t)j * kTilePts, np, sel.warp_cnt[j], run, &sel);
+  if (warp_id() == kSelWarps) {
+    // ---------------- look-back warp ----------------
+    for (uint32_t n = 0;; ++n) {
+      const uint32_t b = n % kSelBufs;
+      const uint32_t par = (n / kSelBufs) & 1u;
+      mbar_wait(&bar_tk[b], par);
+      SelUnit& U = unit[b];
+      const unsigned long long tile = U.tile;
+      if (tile == ~0ull) break;
+      const uint64_t lane_first = U.seg.lane_first_tile;
+      mbar_wait(&bar_cnt[b], par);
+      uint32_t total = ln < (uint32_t)kSelWarps ? U.warp_cnt[ln] : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      // (the unit's aggregate was published by the consumer warp that posted the last count)
+      unsigned long long excl = 0;
+      if (tile != lane_first && !(P.debug & 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
+      if (ln == 0) {
+        if (tile != lane_first) st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
+        U.out_rec = U.out_base + excl;
+        if (total) atomicAdd(U.count, (unsigned long long)total);
+        mbar_arrive(&bar_pre[b]);
       }
-      // select_emit_sub ends with a barrier whenever it read the stage; when it returned early (no match in
-      // the sub-tile) the count phase barrier is the last reader of stage j
-      if (tid == 0) issue(j);
     }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  // iteration n: ballot unit n (its loads were issued one iteration ago), record the matches, post the count
+  // (the last warp to post publishes the aggregate); issue the predicate loads of unit n + 1; emit unit n - 2
+  // while they are in flight.  Counting never waits for a look-back; only the emit does, two units later.
+  const uint32_t w = warp_id();
+  const uint32_t lt = (1u << ln) - 1u;
+  int32_t vx[kSelRows], vy[kSelRows], vz[kSelRows];
+  uint32_t npts = 0;
+
+  auto issue_loads = [&](const SelUnit& U) {
+    const Segment& S = U.seg;
+    npts = U.npts;
+    const uint64_t u0 = U.u0;
+    if (P.query_kind == PCQ_QUERY_BOUNDS) {
+      const uint64_t stride = S.record_len;  // LAST: 12
+#pragma unroll
+      for (int k = 0; k < kSelRows; ++k) {
+        const uint32_t i = min(w * kSelWarpPts + (uint32_t)k * 32u + ln, npts - 1u);  // clamped: always loadable
+        const uint8_t* p = S.rec + (u0 + i) * stride;
+        vx[k] = ldg_i32_a<AL>(p);
+        vy[k] = ldg_i32_a<AL>(p + 4);
+        vz[k] = ldg_i32_a<AL>(p + 8);
+      }
+    } else {
+      const bool las = S.layout == PCQ_LAYOUT_LAS;
+      const uint8_t* cbase = las ? S.rec + S.cls_off : S.cls;
+      const uint64_t stride = las ? (uint64_t)S.record_len : 1ull;
+#pragma unroll
+      for (int k = 0; k < kSelRows; ++k) {
+        const uint32_t i = min(w * kSelWarpPts + (uint32_t)k * 32u + ln, npts - 1u);
+        vx[k] = (int32_t)__ldg(cbase + (u0 + i) * stride);
+        vy[k] = vz[k] = 0;
+      }
+    }
+  };
+
+  mbar_wait(&bar_tk[0], 0u);
+  bool cur = unit[0].tile != ~0ull, prev1 = false, prev2 = false;
+  if (cur) issue_loads(unit[0]);
+  for (uint32_t n = 0;; ++n) {
+    const uint32_t b = n % kSelBufs;
+    if (cur) {
+      SelUnit& U = unit[b];
+      const Segment& S = U.seg;
+      uint16_t* list = match_list[w][n % 3u];
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kSelRows; ++k) {
+        const uint32_t il = (uint32_t)k * 32u + ln;  // index within the warp's 256 records
+        bool m = w * kSelWarpPts + il < npts;
+        if (P.query_kind == PCQ_QUERY_BOUNDS)
+          m = m & in_range(vx[k], S.lo[0], S.hi[0]) & in_range(vy[k], S.lo[1], S.hi[1]) & in_range(vz[k], S.lo[2], S.hi[2]);
+        else
+          m = m & ((uint32_t)vx[k] == P.cls);
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (m) list[cnt + (uint32_t)__popc(bal & lt)] = (uint16_t)il;
+        cnt += (uint32_t)__popc(bal);
+      }
+      __syncwarp();  // the list is read by other lanes two iterations later
+      if (ln == 0) {
+        U.warp_cnt[w] = cnt;
+        // The warp that posts the last count publishes the unit's aggregate right away: no look-back of another
+        // CTA ever waits behind one of this CTA's look-backs.
+        const uint32_t old = atomicAdd(&U.acc, cnt + (1u << 24));
+        if ((old >> 24) == (uint32_t)kSelWarps - 1u) {
+          const unsigned long long total = (unsigned long long)((old & 0xFFFFFFu) + cnt);
+          const unsigned long long st = U.tile == S.lane_first_tile ? kStPrefix : kStAgg;  // first unit: prefix == aggregate
+          st_state(P.tile_state + U.tile, (st << kStatusShift) | total);
+        }
+        mbar_arrive(&bar_cnt[b]);
+      }
+    }
+    bool nxt = false;
+    if (cur) {
+      const uint32_t nb = (n + 1u) % kSelBufs;
+      mbar_wait(&bar_tk[nb], ((n + 1u) / kSelBufs) & 1u);
+      nxt = unit[nb].tile != ~0ull;
+      if (nxt) issue_loads(unit[nb]);
+    }
+    if (prev2) {
+      const uint32_t pb = (n - 2u) % kSelBufs;
+      mbar_wait(&bar_pre[pb], ((n - 2u) / kSelBufs) & 1u);
+      if (!(P.debug & 2u)) select_emit_warp<AL>(unit[pb], match_list[w][(n - 2u) % 3u], stage[w]);
+      __syncwarp();
+      if (ln == 0) mbar_arrive(&bar_free[pb]);
+    }
+    if (!cur && !prev1) break;
+    prev2 = prev1;
+    prev1 = cur;
+    cur = nxt;
   }
 }
 
@@ -1108,12 +1218,6 @@ template <int R>
 struct ScanStages {
   static constexpr int value = R <= 12 ? 8 : (R <= 20 ? 6 : 4);
 };
-// group size (= ring depth) of the select kernels: ~50-70 KB ring, two CTAs per SM
-template <int R>
-struct SelectGroup {
-  static constexpr int value = R <= 12 ? 8 : (R <= 20 ? 6 : (R <= 28 ? 5 : 4));
-};
-
 static int persistent_grid(const void* kfn, size_t smem, int sm_count, uint64_t n_tiles, int max_per_sm, unsigned* grid_out) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBlock, smem) != cudaSuccess) return -1;
@@ -1142,23 +1246,6 @@ static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   return check_launch();
 }
 
-template <int R>
-static int launch_select_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
-  constexpr int G = SelectGroup<R>::value;
-  constexpr size_t smem = (size_t)G * kTilePts * R;
-  static bool configured = false;
-  auto kfn = k_select_staged<R, G>;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = true;
-  }
-  unsigned grid = 0;
-  if (persistent_grid((const void*)kfn, smem, sm_count, p.n_tiles, 3, &grid) != 0) return -1;
-  if (grid == 0) return 0;
-  kfn<<<grid, kBlock, smem, st>>>(p);
-  return check_launch();
-}
-
 template <int MODE>
 static int launch_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
   switch (R) {
@@ -1168,17 +1255,6 @@ static int launch_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaSt
     case 28: return launch_staged_t<28, MODE>(p, sm_count, st);
     case 34: return launch_staged_t<34, MODE>(p, sm_count, st);
     default: return 1;  // not instantiated
-  }
-}
-
-static int launch_select_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
-  switch (R) {
-    case 12: return launch_select_staged_t<12>(p, sm_count, st);
-    case 20: return launch_select_staged_t<20>(p, sm_count, st);
-    case 26: return launch_select_staged_t<26>(p, sm_count, st);
-    case 28: return launch_select_staged_t<28>(p, sm_count, st);
-    case 34: return launch_select_staged_t<34>(p, sm_count, st);
-    default: return 1;
   }
 }
 
@@ -1192,43 +1268,46 @@ static int launch_direct_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   return check_launch();
 }
 
-static int launch_select_direct(const ScanParams& p, int sm_count, cudaStream_t st) {
+template <int AL>
+static int launch_select_t(const ScanParams& p, int sm_count, cudaStream_t st) {
+  auto kfn = k_select<AL>;
   unsigned grid = 0;
-  if (persistent_grid((const void*)k_select_direct, 0, sm_count, p.n_tiles, 8, &grid) != 0) return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kSelThreads, 0) != cudaSuccess) return -1;
+  if (per_sm < 1) per_sm = 1;
+  uint64_t g = (uint64_t)sm_count * (uint64_t)per_sm;  // persistent: every CTA resident at once
+  if (g > p.n_tiles) g = p.n_tiles;
+  grid = (unsigned)g;
   if (grid == 0) return 0;
-  k_select_direct<<<grid, kBlock, 0, st>>>(p);
+  kfn<<<grid, kSelThreads, 0, st>>>(p);
   return check_launch();
+}
+// `align` = alignment every x/y/z field of every segment of the launch is guaranteed to have (4, 2 or 1)
+static int launch_select(const ScanParams& p, int align, int sm_count, cudaStream_t st) {
+  if (align >= 4) return launch_select_t<4>(p, sm_count, st);
+  if (align >= 2) return launch_select_t<2>(p, sm_count, st);
+  return launch_select_t<1>(p, sm_count, st);
 }
 
 bool staged_supports(uint32_t R) { return R == 12 || R == 20 || R == 26 || R == 28 || R == 34; }
 
-// records per scheduling unit ("tile") for a launch: 512 for count / grid, a whole group for select
-uint32_t tile_points(int variant, int mode, uint32_t R) {
-  if (mode != MODE_SELECT) return kTilePts;
-  if (variant == 2 && staged_supports(R)) {
-    switch (R) {
-      case 12: return kTilePts * SelectGroup<12>::value;
-      case 20: return kTilePts * SelectGroup<20>::value;
-      case 26: return kTilePts * SelectGroup<26>::value;
-      case 28: return kTilePts * SelectGroup<28>::value;
-      default: return kTilePts * SelectGroup<34>::value;
-    }
-  }
-  return kTilePts * kMaxGroup;
+// records per scheduling unit ("tile") for a launch: 512 for count / grid, a look-back unit for select
+uint32_t tile_points(int /*variant*/, int mode, uint32_t /*R*/) {
+  return mode == MODE_SELECT ? (uint32_t)kSelUnitPts : (uint32_t)kTilePts;
 }
 
 // variant: 1 = direct, 2 = staged (needs uniform_record_len supported); returns 0 ok, <0 CUDA error
-int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int sm_count, void* stream) {
+int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int min_align, int sm_count,
+                void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == MODE_SELECT) return launch_select(p, min_align, sm_count, st);  // one kernel family serves every layout
   if (variant == 2 && staged_supports(uniform_record_len)) {
     int rc = 1;
     if (mode == MODE_COUNT) rc = launch_staged_r<MODE_COUNT>(p, uniform_record_len, sm_count, st);
-    if (mode == MODE_SELECT) rc = launch_select_staged_r(p, uniform_record_len, sm_count, st);
     if (mode == MODE_GRID) rc = launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
     if (rc <= 0) return rc;
   }
   if (mode == MODE_COUNT) return launch_direct_t<MODE_COUNT>(p, sm_count, st);
-  if (mode == MODE_SELECT) return launch_select_direct(p, sm_count, st);
   return launch_direct_t<MODE_GRID>(p, sm_count, st);
 }
 

@@ -36,7 +36,8 @@ struct alignas(16) Segment {
   int16_t rgb_off;      // LAS: offset of the colour inside a record, -1 if the format has none
   uint8_t layout;       // pcq_layout
   uint8_t align;        // 4, 2 or 1: alignment every x/y/z field of the range is guaranteed to have
-  uint8_t pad_[2];
+  uint8_t rgb_align2;   // LAST: 1 when the colour column of the range is 2-byte aligned
+  uint8_t pad_[1];
 };
 
 // 64-byte density candidate == pcq_cell_candidate of the C ABI.
@@ -91,12 +92,14 @@ struct ScanParams {
   const LaneDev* lanes;
   unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
   unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
+  uint32_t debug;                  // measurement only (PCQ_SELECT_DEBUG): 1 = skip the look-back, 2 = skip the emit
 };
 
 // launch wrappers implemented in kernels.cu (stream is a cudaStream_t); 0 = ok, < 0 = CUDA error
 bool staged_supports(uint32_t record_len);
 uint32_t tile_points(int variant, int mode, uint32_t record_len);
-int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int sm_count, void* stream);
+int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int min_align, int sm_count,
+                void* stream);
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
 int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count, int sm_count,
                       void* stream);
