@@ -682,8 +682,10 @@ constexpr int kSelWarps = 8;
 constexpr int kSelRows = 8;
 constexpr int kSelWarpPts = 32 * kSelRows;
 constexpr int kSelUnitPts = kSelWarps * kSelWarpPts;  // 2048
-constexpr int kSelThreads = (kSelWarps + 2) * 32;  // + look-back warp + dispatcher warp
-constexpr int kSelBufs = 6;        // unit descriptors per CTA: n-2 (emit) .. n+1 (loads) + two ticketed ahead
+constexpr int kSelLbWarps = 1;      // look-back warps per CTA (unit n is resolved by warp n % kSelLbWarps)
+constexpr int kSelThreads = (kSelWarps + kSelLbWarps + 1) * 32;  // + look-back warps + dispatcher warp
+constexpr int kSelLag = 3;         // a unit is emitted this many units behind the counted front
+constexpr int kSelBufs = 8;        // unit descriptors per CTA: n-2 (emit) .. n+1 (loads) + two ticketed ahead
 constexpr int kSelStageRecs = 64;  // records composed per flush round of a warp
 constexpr int kSelStageBytes = 2048;  // 64 * 31 + 15 phase bytes, rounded up
 
@@ -701,30 +703,77 @@ struct SelUnit {
   uint32_t warp_cnt[kSelWarps];
 };
 
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// L2 cache policies.  The select kernel reads every record once from HBM (`keep`: evict_last) and re-reads the
+// matching ones from L2 a few microseconds later when it emits them (`drop`: evict_first, like the output stores),
+// so that neither the re-read nor the 31-byte output stream pushes not-yet-emitted records out of L2.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ldg_u32_h(const uint8_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u16_h(const uint8_t* p, uint64_t pol) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+  return (uint32_t)v;
+}
+__device__ __forceinline__ uint32_t ldg_u8_h(const uint8_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_v4_h(uint4* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void stg_u8_h(uint8_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // loads of little-endian fields whose alignment AL (4, 2 or 1) is a compile-time constant
 template <int AL>
-__device__ __forceinline__ int32_t ldg_i32_a(const uint8_t* p) {
+__device__ __forceinline__ int32_t ldg_i32_a(const uint8_t* p, uint64_t pol) {
   if constexpr (AL == 4) {
-    return __ldg(reinterpret_cast<const int32_t*>(p));
+    return (int32_t)ldg_u32_h(p, pol);
   } else if constexpr (AL == 2) {
-    const uint32_t a = __ldg(reinterpret_cast<const uint16_t*>(p));
-    const uint32_t b = __ldg(reinterpret_cast<const uint16_t*>(p + 2));
-    return (int32_t)(a | (b << 16));
+    return (int32_t)(ldg_u16_h(p, pol) | (ldg_u16_h(p + 2, pol) << 16));
   } else {
-    const uint32_t b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
-    return (int32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+    return (int32_t)(ldg_u8_h(p, pol) | (ldg_u8_h(p + 1, pol) << 8) | (ldg_u8_h(p + 2, pol) << 16) | (ldg_u8_h(p + 3, pol) << 24));
   }
 }
 template <int AL>
-__device__ __forceinline__ uint32_t ldg_u16_a(const uint8_t* p) {
+__device__ __forceinline__ uint32_t ldg_u16_a(const uint8_t* p, uint64_t pol) {
   if constexpr (AL >= 2) {
-    return __ldg(reinterpret_cast<const uint16_t*>(p));
+    return ldg_u16_h(p, pol);
   } else {
-    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8);
+    return ldg_u8_h(p, pol) | (ldg_u8_h(p + 1, pol) << 8);
   }
 }
 
@@ -735,49 +784,50 @@ struct RawPoint {
 
 // all fields of two records at once (14 independent loads per lane in flight)
 template <int AL>
-__device__ __forceinline__ void select_fetch2(const Segment& S, uint64_t i0, uint64_t i1, RawPoint& a, RawPoint& b) {
+__device__ __forceinline__ void select_fetch2(const Segment& S, uint64_t i0, uint64_t i1, RawPoint& a, RawPoint& b,
+                                              uint64_t pol) {
   const uint8_t* p0 = S.rec + i0 * (uint64_t)S.record_len;  // LAST: record_len == 12 (positions column)
   const uint8_t* p1 = S.rec + i1 * (uint64_t)S.record_len;
-  a.x = ldg_i32_a<AL>(p0);
-  a.y = ldg_i32_a<AL>(p0 + 4);
-  a.z = ldg_i32_a<AL>(p0 + 8);
-  b.x = ldg_i32_a<AL>(p1);
-  b.y = ldg_i32_a<AL>(p1 + 4);
-  b.z = ldg_i32_a<AL>(p1 + 8);
+  a.x = ldg_i32_a<AL>(p0, pol);
+  a.y = ldg_i32_a<AL>(p0 + 4, pol);
+  a.z = ldg_i32_a<AL>(p0 + 8, pol);
+  b.x = ldg_i32_a<AL>(p1, pol);
+  b.y = ldg_i32_a<AL>(p1 + 4, pol);
+  b.z = ldg_i32_a<AL>(p1 + 8, pol);
   a.r = a.g = a.b = b.r = b.g = b.b = 0u;  // Vector3::new(0, 0, 0), las.rs:134
   if (S.layout == PCQ_LAYOUT_LAS) {
-    a.cls = __ldg(p0 + S.cls_off);
-    b.cls = __ldg(p1 + S.cls_off);
+    a.cls = ldg_u8_h(p0 + S.cls_off, pol);
+    b.cls = ldg_u8_h(p1 + S.cls_off, pol);
     if (S.rgb_off >= 0) {
       const uint8_t* c0 = p0 + (uint32_t)S.rgb_off;  // 20 / 28: as aligned as the record itself (up to 2)
       const uint8_t* c1 = p1 + (uint32_t)S.rgb_off;
-      a.r = ldg_u16_a<AL>(c0);
-      a.g = ldg_u16_a<AL>(c0 + 2);
-      a.b = ldg_u16_a<AL>(c0 + 4);
-      b.r = ldg_u16_a<AL>(c1);
-      b.g = ldg_u16_a<AL>(c1 + 2);
-      b.b = ldg_u16_a<AL>(c1 + 4);
+      a.r = ldg_u16_a<AL>(c0, pol);
+      a.g = ldg_u16_a<AL>(c0 + 2, pol);
+      a.b = ldg_u16_a<AL>(c0 + 4, pol);
+      b.r = ldg_u16_a<AL>(c1, pol);
+      b.g = ldg_u16_a<AL>(c1 + 2, pol);
+      b.b = ldg_u16_a<AL>(c1 + 4, pol);
     }
   } else {
-    a.cls = __ldg(S.cls + i0);
-    b.cls = __ldg(S.cls + i1);
+    a.cls = ldg_u8_h(S.cls + i0, pol);
+    b.cls = ldg_u8_h(S.cls + i1, pol);
     if (S.rgb != nullptr) {
       const uint8_t* c0 = S.rgb + i0 * 6ull;
       const uint8_t* c1 = S.rgb + i1 * 6ull;
       if (S.rgb_align2) {
-        a.r = ldg_u16_a<2>(c0);
-        a.g = ldg_u16_a<2>(c0 + 2);
-        a.b = ldg_u16_a<2>(c0 + 4);
-        b.r = ldg_u16_a<2>(c1);
-        b.g = ldg_u16_a<2>(c1 + 2);
-        b.b = ldg_u16_a<2>(c1 + 4);
+        a.r = ldg_u16_a<2>(c0, pol);
+        a.g = ldg_u16_a<2>(c0 + 2, pol);
+        a.b = ldg_u16_a<2>(c0 + 4, pol);
+        b.r = ldg_u16_a<2>(c1, pol);
+        b.g = ldg_u16_a<2>(c1 + 2, pol);
+        b.b = ldg_u16_a<2>(c1 + 4, pol);
       } else {
-        a.r = ldg_u16_a<1>(c0);
-        a.g = ldg_u16_a<1>(c0 + 2);
-        a.b = ldg_u16_a<1>(c0 + 4);
-        b.r = ldg_u16_a<1>(c1);
-        b.g = ldg_u16_a<1>(c1 + 2);
-        b.b = ldg_u16_a<1>(c1 + 4);
+        a.r = ldg_u16_a<1>(c0, pol);
+        a.g = ldg_u16_a<1>(c0 + 2, pol);
+        a.b = ldg_u16_a<1>(c0 + 4, pol);
+        b.r = ldg_u16_a<1>(c1, pol);
+        b.g = ldg_u16_a<1>(c1 + 2, pol);
+        b.b = ldg_u16_a<1>(c1 + 4, pol);
       }
     }
   }
@@ -807,6 +857,14 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
   const unsigned long long out0 = U.out_rec + before;
   const Segment& S = U.seg;
   const uint64_t wbase = U.u0 + (uint64_t)w * kSelWarpPts;
+  const uint64_t pol = l2_policy_drop();
+  // the fields of round r + 1 are fetched (L2) while round r is composed and flushed
+  RawPoint q0, q1;
+  {
+    const uint32_t n = min((uint32_t)kSelStageRecs, mine);
+    // lanes beyond the round's records fetch the round's first record again (always a valid address)
+    select_fetch2<AL>(S, wbase + list[ln < n ? ln : 0u], wbase + list[ln + 32u < n ? ln + 32u : 0u], q0, q1, pol);
+  }
 #pragma unroll 1
   for (uint32_t base = 0; base < mine; base += kSelStageRecs) {
     const unsigned long long orec = out0 + base;
@@ -814,13 +872,14 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
     const uint32_t phase = (uint32_t)(g0 & 15ull);   // keep global and shared 16-byte phases equal
     const uint32_t n = min((uint32_t)kSelStageRecs, mine - base);
     const uint32_t r0 = ln, r1 = ln + 32u;
-    // lanes beyond the round's records fetch the round's first record again (always a valid address)
-    const uint64_t i0 = wbase + list[base + (r0 < n ? r0 : 0u)];
-    const uint64_t i1 = wbase + list[base + (r1 < n ? r1 : 0u)];
-    RawPoint q0, q1;
-    select_fetch2<AL>(S, i0, i1, q0, q1);
-    if (r0 < n) select_compose(S, q0, stage + phase + r0 * 31u);
-    if (r1 < n) select_compose(S, q1, stage + phase + r1 * 31u);
+    RawPoint p0 = q0, p1 = q1;
+    if (base + kSelStageRecs < mine) {
+      const uint32_t nbase = base + kSelStageRecs;
+      const uint32_t nn = min((uint32_t)kSelStageRecs, mine - nbase);
+      select_fetch2<AL>(S, wbase + list[nbase + (r0 < nn ? r0 : 0u)], wbase + list[nbase + (r1 < nn ? r1 : 0u)], q0, q1, pol);
+    }
+    if (r0 < n) select_compose(S, p0, stage + phase + r0 * 31u);
+    if (r1 < n) select_compose(S, p1, stage + phase + r1 * 31u);
     __syncwarp();
     // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
     const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
@@ -829,12 +888,12 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
       uint8_t* gbase = U.out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
       const uint32_t end = phase + nb;
       const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;  // full 16-byte chunks [c_first, c_end)
-      if (phase + ln < (c_first << 4)) gbase[phase + ln] = stage[phase + ln];
+      if (phase + ln < (c_first << 4)) stg_u8_h(gbase + phase + ln, stage[phase + ln], pol);
       const uint4* sv = reinterpret_cast<const uint4*>(stage);
       uint4* gv = reinterpret_cast<uint4*>(gbase);
-      for (uint32_t c = c_first + ln; c < c_end; c += 32u) gv[c] = sv[c];
+      for (uint32_t c = c_first + ln; c < c_end; c += 32u) stg_v4_h(gv + c, sv[c], pol);
       const uint32_t tb = (c_end << 4) + ln;
-      if (tb < end) gbase[tb] = stage[tb];
+      if (tb < end) stg_u8_h(gbase + tb, stage[tb], pol);
     }
     __syncwarp();  // the staging buffer is reused by the next round / unit
   }
@@ -848,7 +907,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
   __shared__ __align__(8) uint64_t bar_pre[kSelBufs];   // exclusive prefix resolved (look-back warp -> consumers)
   __shared__ __align__(8) uint64_t bar_free[kSelBufs];  // unit emitted              (consumers -> dispatcher)
   __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
-  __shared__ uint16_t match_list[kSelWarps][3][kSelWarpPts];  // unit-local index of each warp's r-th match
+  __shared__ uint16_t match_list[kSelWarps][kSelLag + 1][kSelWarpPts];  // unit-local index of each warp's r-th match
 
   const uint32_t ln = lane_id();
   if (threadIdx.x == 0) {
@@ -863,15 +922,18 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
   }
   __syncthreads();
 
-  if (warp_id() == kSelWarps + 1) {
+  if (warp_id() == kSelWarps + kSelLbWarps) {
     // ---------------- dispatcher warp: tickets and unit descriptors, never blocked by a look-back ----------------
     uint32_t seg_cur = 0;
+    uint32_t end_marks = 0;  // every look-back warp needs to meet an end marker
     for (uint32_t n = 0;; ++n) {
       const uint32_t b = n % kSelBufs;
       if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
-      unsigned long long tile = 0;
-      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
+      unsigned long long tile = ~0ull;
+      if (end_marks == 0u) {
+        if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      }
       SelUnit& U = unit[b];
       if (ln == 0) U.acc = 0u;
       if (tile >= P.n_tiles) {
@@ -879,7 +941,8 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
           U.tile = ~0ull;
           mbar_arrive(&bar_tk[b]);
         }
-        break;
+        if (++end_marks == (uint32_t)kSelLbWarps) break;
+        continue;
       }
       while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
       const Segment* sg = P.segs + seg_cur;
@@ -904,9 +967,9 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
     return;
   }
 
-  if (warp_id() == kSelWarps) {
-    // ---------------- look-back warp ----------------
-    for (uint32_t n = 0;; ++n) {
+  if (warp_id() >= kSelWarps) {
+    // ---------------- look-back warps: one look-back takes a few L2 round trips, so two run interleaved ----------------
+    for (uint32_t n = warp_id() - kSelWarps;; n += kSelLbWarps) {
       const uint32_t b = n % kSelBufs;
       const uint32_t par = (n / kSelBufs) & 1u;
       mbar_wait(&bar_tk[b], par);
@@ -940,6 +1003,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
   int32_t vx[kSelRows], vy[kSelRows], vz[kSelRows];
   uint32_t npts = 0;
 
+  const uint64_t pol_keep = l2_policy_keep();
   auto issue_loads = [&](const SelUnit& U) {
     const Segment& S = U.seg;
     npts = U.npts;
@@ -950,9 +1014,9 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
       for (int k = 0; k < kSelRows; ++k) {
         const uint32_t i = min(w * kSelWarpPts + (uint32_t)k * 32u + ln, npts - 1u);  // clamped: always loadable
         const uint8_t* p = S.rec + (u0 + i) * stride;
-        vx[k] = ldg_i32_a<AL>(p);
-        vy[k] = ldg_i32_a<AL>(p + 4);
-        vz[k] = ldg_i32_a<AL>(p + 8);
+        vx[k] = ldg_i32_a<AL>(p, pol_keep);
+        vy[k] = ldg_i32_a<AL>(p + 4, pol_keep);
+        vz[k] = ldg_i32_a<AL>(p + 8, pol_keep);
       }
     } else {
       const bool las = S.layout == PCQ_LAYOUT_LAS;
@@ -961,21 +1025,22 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
 #pragma unroll
       for (int k = 0; k < kSelRows; ++k) {
         const uint32_t i = min(w * kSelWarpPts + (uint32_t)k * 32u + ln, npts - 1u);
-        vx[k] = (int32_t)__ldg(cbase + (u0 + i) * stride);
+        vx[k] = (int32_t)ldg_u8_h(cbase + (u0 + i) * stride, pol_keep);
         vy[k] = vz[k] = 0;
       }
     }
   };
 
   mbar_wait(&bar_tk[0], 0u);
-  bool cur = unit[0].tile != ~0ull, prev1 = false, prev2 = false;
+  bool cur = unit[0].tile != ~0ull;
   if (cur) issue_loads(unit[0]);
+  uint32_t emit_next = 0;  // oldest unit of this CTA that this warp has not emitted yet
   for (uint32_t n = 0;; ++n) {
     const uint32_t b = n % kSelBufs;
     if (cur) {
       SelUnit& U = unit[b];
       const Segment& S = U.seg;
-      uint16_t* list = match_list[w][n % 3u];
+      uint16_t* list = match_list[w][n % (uint32_t)(kSelLag + 1)];
       uint32_t cnt = 0;
 #pragma unroll
       for (int k = 0; k < kSelRows; ++k) {
@@ -989,7 +1054,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
         if (m) list[cnt + (uint32_t)__popc(bal & lt)] = (uint16_t)il;
         cnt += (uint32_t)__popc(bal);
       }
-      __syncwarp();  // the list is read by other lanes two iterations later
+      __syncwarp();  // the list is read by other lanes when the unit is emitted
       if (ln == 0) {
         U.warp_cnt[w] = cnt;
         // The warp that posts the last count publishes the unit's aggregate right away: no look-back of another
@@ -1003,6 +1068,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
         mbar_arrive(&bar_cnt[b]);
       }
     }
+    const uint32_t counted = cur ? n + 1u : n;  // units [0, counted) of this CTA are counted
     bool nxt = false;
     if (cur) {
       const uint32_t nb = (n + 1u) % kSelBufs;
@@ -1010,16 +1076,24 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
       nxt = unit[nb].tile != ~0ull;
       if (nxt) issue_loads(unit[nb]);
     }
-    if (prev2) {
-      const uint32_t pb = (n - 2u) % kSelBufs;
-      mbar_wait(&bar_pre[pb], ((n - 2u) / kSelBufs) & 1u);
-      if (!(P.debug & 2u)) select_emit_warp<AL>(unit[pb], match_list[w][(n - 2u) % 3u], stage[w]);
+    // Emit while the loads of unit n + 1 are in flight: units two or more behind the counted front must go now
+    // (their match list and descriptor are about to be reused); a younger unit goes early when its prefix is
+    // already there, which keeps the records it re-reads resident in L2.  After the last unit everything goes.
+    while (emit_next < counted) {
+      const uint32_t pb = emit_next % kSelBufs;
+      const uint32_t par = (emit_next / kSelBufs) & 1u;
+      const bool must = !nxt || emit_next + (uint32_t)kSelLag < counted;
+      if (must) {
+        mbar_wait(&bar_pre[pb], par);
+      } else if (!(P.debug & 4u) || !mbar_test(&bar_pre[pb], par)) {
+        break;  // (debug 4: emit a younger unit early when its prefix is already there)
+      }
+      if (!(P.debug & 2u)) select_emit_warp<AL>(unit[pb], match_list[w][emit_next % (uint32_t)(kSelLag + 1)], stage[w]);
       __syncwarp();
       if (ln == 0) mbar_arrive(&bar_free[pb]);
+      ++emit_next;
     }
-    if (!cur && !prev1) break;
-    prev2 = prev1;
-    prev1 = cur;
+    if (!nxt) break;
     cur = nxt;
   }
 }

@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 28)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--only", default="")
+    ap.add_argument("--cases", default="", help="comma list of layout:format, e.g. las:1,last:3")
+    ap.add_argument("--select-queries", default="", help="comma list out of 1pct,50pct,100pct")
+    ap.add_argument("--variants", default="2,1", help="scan variants to run: 2 = staged, 1 = direct")
     args = ap.parse_args()
 
     import torch
@@ -56,6 +59,9 @@ def main():
         run_configs(pcq, ctx, stream, timed, peak, args)
         return
     cases = [("las", 0), ("las", 1), ("las", 2), ("las", 3), ("last", 1), ("last", 3)]
+    if args.cases:  # e.g. --cases las:1,last:3
+        cases = [(c.split(":")[0], int(c.split(":")[1])) for c in args.cases.split(",")]
+    sel_names = tuple(args.select_queries.split(",")) if args.select_queries else ("1pct", "50pct", "100pct")
     for ext, fmt in cases:
         layout = B.LAYOUT_LAS if ext == "las" else B.LAYOUT_LAST
         sp = S.uniform_spec(N, layout, fmt, extent=1_000_000)
@@ -67,7 +73,7 @@ def main():
         read_class = R if ext == "las" else 1
         # boxes with ~50 %, ~1 % and 100 % selectivity (uniform cube of 10 km at scale 0.01)
         boxes = {"50pct": ((0, 0, 0), (10000.0, 10000.0, 5000.0)), "1pct": ((0, 0, 0), (2154.0, 2154.0, 2154.0)), "100pct": ((-1, -1, -1), (10001.0, 10001.0, 10001.0))}
-        for variant in (2, 1):
+        for variant in [int(v) for v in args.variants.split(",")]:
             ctx.set_scan_variant(variant)
             vname = {1: "direct", 2: "staged"}[variant]
 
@@ -99,7 +105,7 @@ def main():
                 emit("class_2", "count", ms, read_class, c.point_count())
             # ---- select (BufferCollector) ----
             if not args.only or args.only in ("select", "all"):
-                for name in ("1pct", "50pct", "100pct"):
+                for name in sel_names:
                     c = pcq.BufferCollector(ctx)
                     s = pcq.BoundsSearcher(*boxes[name])
 
