@@ -369,12 +369,19 @@ struct CellEval {
 };
 
 __device__ __forceinline__ CellEval grid_eval(const GridDev& g, double px, double py, double pz) {
-  // :51-56  r = (p - min) * dims as f64 / (max - min)
-  double rx = __ddiv_rn(__dmul_rn(__dsub_rn(px, g.bmin[0]), g.dims_f[0]), __dsub_rn(g.bmax[0], g.bmin[0]));
-  double ry = __ddiv_rn(__dmul_rn(__dsub_rn(py, g.bmin[1]), g.dims_f[1]), __dsub_rn(g.bmax[1], g.bmin[1]));
-  double rz = __ddiv_rn(__dmul_rn(__dsub_rn(pz, g.bmin[2]), g.dims_f[2]), __dsub_rn(g.bmax[2], g.bmin[2]));
-  // :58-60
-  uint64_t cx = f64_as_u64(rx), cy = f64_as_u64(ry), cz = f64_as_u64(rz);
+  // :51-56  r = (p - min) * dims as f64 / (max - min);  :58-60  cell = r as u64
+  // A zero numerator (a point exactly on a minimum face — common on synthetic and on clipped data) sends the
+  // whole warp through the slow path of the IEEE division; 0 / d is 0 or NaN and both cast to cell 0, so such
+  // lanes divide 1.0 instead and ignore the quotient.
+  const double nx = __dmul_rn(__dsub_rn(px, g.bmin[0]), g.dims_f[0]);
+  const double ny = __dmul_rn(__dsub_rn(py, g.bmin[1]), g.dims_f[1]);
+  const double nz = __dmul_rn(__dsub_rn(pz, g.bmin[2]), g.dims_f[2]);
+  const double rx = __ddiv_rn(nx == 0.0 ? 1.0 : nx, __dsub_rn(g.bmax[0], g.bmin[0]));
+  const double ry = __ddiv_rn(ny == 0.0 ? 1.0 : ny, __dsub_rn(g.bmax[1], g.bmin[1]));
+  const double rz = __ddiv_rn(nz == 0.0 ? 1.0 : nz, __dsub_rn(g.bmax[2], g.bmin[2]));
+  const uint64_t cx = nx == 0.0 ? 0ull : f64_as_u64(rx);
+  const uint64_t cy = ny == 0.0 ? 0ull : f64_as_u64(ry);
+  const uint64_t cz = nz == 0.0 ? 0ull : f64_as_u64(rz);
   CellEval e;
   // a cell above its mask aliases a low cell while its centre lies elsewhere (:62-70 vs :78-82)
   e.aliased = (cx > g.mask[0]) | (cy > g.mask[1]) | (cz > g.mask[2]);
@@ -390,61 +397,122 @@ __device__ __forceinline__ CellEval grid_eval(const GridDev& g, double px, doubl
   return e;
 }
 
-// Warp-convergent: every lane calls it, `m` says whether this lane carries a matching point.
+// Candidate arena allocation.  One global counter bumped once per warp and append serialises on its L2 atomic
+// unit (it was a quarter of the insert kernel's time); instead every warp owns a private chunk of kCandChunk
+// slots, fills it without any atomic and takes a new chunk with ONE atomicAdd when it is full.  Slots a warp
+// reserved but did not use are marked empty (scan_idx == ~0) and skipped by every consumer of the arena.
+constexpr uint32_t kCandChunk = 128;
+constexpr unsigned long long kCandEmpty = ~0ull;
+
+struct CandChunk {
+  unsigned long long base = 0;
+  uint32_t used = kCandChunk;  // == kCandChunk: no chunk yet
+};
+
+__device__ __forceinline__ void cand_pad(const GridDev& g, const CandChunk& ch) {
+  for (uint32_t i = ch.used + lane_id(); i < kCandChunk; i += 32u) {
+    const unsigned long long ci = ch.base + i;
+    if (ci < g.cand_cap) g.cands[ci].scan_idx = kCandEmpty;
+  }
+}
+
+struct LaneChunk {  // a warp's chunk belongs to the arena of one lane (collector)
+  CandChunk c;
+  uint32_t lane = 0xFFFFFFFFu;
+};
+
+// all 32 lanes; n (1..32) is warp-uniform; returns the arena index of the group's first slot
+__device__ __forceinline__ unsigned long long cand_reserve(const GridDev& g, CandChunk& ch, uint32_t n) {
+  if (ch.used + n > kCandChunk) {
+    cand_pad(g, ch);
+    unsigned long long nb = 0;
+    if (lane_id() == 0) nb = atomicAdd(g.cand_count, (unsigned long long)kCandChunk);
+    ch.base = __shfl_sync(0xffffffffu, nb, 0);
+    ch.used = 0;
+  }
+  const unsigned long long r = ch.base + ch.used;
+  ch.used += n;
+  return r;
+}
+
+// Warp-convergent: every lane calls it; m[j] says whether this lane's j-th point of the tile matches.
 // A point survives as a candidate iff its distance is <= the cell minimum seen so far; the true
 // winner (smallest distance, then smallest scan index == the strict `<` fold of :97-102) always is.
+// The kPPT points of a lane are taken through each step together so that their table reads (random
+// accesses into a table far larger than L2) are in flight at the same time.
 template <class Src>
-__device__ __forceinline__ void grid_insert(const GridDev& g, const Segment& S, const Src& src, bool m,
-                                            const Hit& h, uint64_t idx, uint32_t i_in_tile) {
-  bool want = false;
-  CellEval e;
-  e.key = 0;
-  e.dist_bits = 0;
-  e.aliased = false;
-  if (m) {
-    double px = reconstruct(h.x, S.scale[0], S.offset[0]);
-    double py = reconstruct(h.y, S.scale[1], S.offset[1]);
-    double pz = reconstruct(h.z, S.scale[2], S.offset[2]);
-    e = grid_eval(g, px, py, pz);
-    if (e.aliased) {
-      atomicOr(g.flags, kFlagAliased);
-    } else {
-      uint64_t slot = grid_slot(g, e.key, true);
-      if (slot == ~0ull) {
-        atomicOr(g.flags, kFlagHashFull);
+__device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment& S, const Src& src, const bool (&m)[kPPT],
+                                                 const Hit (&h)[kPPT], uint64_t p0, CandChunk& ch) {
+  bool any_m = false;
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) any_m |= m[j];
+  if (!__any_sync(0xffffffffu, any_m)) return;  // most tiles of a small query box hold no match at all
+  CellEval e[kPPT];
+  uint64_t slot[kPPT];
+  bool live[kPPT];
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    live[j] = false;
+    slot[j] = 0;
+    e[j].key = 0;
+    e[j].dist_bits = 0;
+    e[j].aliased = false;
+    if (m[j]) {
+      const double px = reconstruct(h[j].x, S.scale[0], S.offset[0]);
+      const double py = reconstruct(h[j].y, S.scale[1], S.offset[1]);
+      const double pz = reconstruct(h[j].z, S.scale[2], S.offset[2]);
+      e[j] = grid_eval(g, px, py, pz);
+      if (e[j].aliased) {
+        atomicOr(g.flags, kFlagAliased);
       } else {
-        // The cell minimum only ever decreases, so a (possibly stale) plain read that is already smaller than
-        // this point's distance proves the point can never win: skip the atomic.  In dense data (many points
-        // per cell) that removes most of the read-modify-write traffic.
-        const unsigned long long seen = __ldcg(g.table + slot);
-        if (e.dist_bits <= seen) {
-          const unsigned long long old = atomicMin(g.table + slot, e.dist_bits);
-          want = e.dist_bits <= old;
-        }
+        slot[j] = grid_slot(g, e[j].key, true);
+        if (slot[j] == ~0ull)
+          atomicOr(g.flags, kFlagHashFull);
+        else
+          live[j] = true;
       }
     }
   }
-  const uint32_t bal = __ballot_sync(0xffffffffu, want);
-  if (bal == 0u) return;
-  const uint32_t leader = (uint32_t)__ffs((int)bal) - 1u;
-  unsigned long long base = 0;
-  if (lane_id() == leader) base = atomicAdd(g.cand_count, (unsigned long long)__popc(bal));
-  base = __shfl_sync(0xffffffffu, base, (int)leader);
-  if (want) {
-    const unsigned long long ci = base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u));
-    if (ci < g.cand_cap) {
-      uint32_t rgb[3];
-      src.colour(S, idx, i_in_tile, rgb);
-      uint32_t w[8];
-      point_words(S, h, rgb, w);
-      uint4* c4 = reinterpret_cast<uint4*>(g.cands + ci);
-      const unsigned long long gidx = S.scan_base + idx;
-      c4[0] = make_uint4((uint32_t)e.key, (uint32_t)(e.key >> 32), (uint32_t)e.dist_bits, (uint32_t)(e.dist_bits >> 32));
-      c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
-      c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
-      c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
-    } else {
-      atomicOr(g.flags, kFlagCandOverflow);
+  // The cell minimum only ever decreases, so a (possibly stale) plain read that is already smaller than this
+  // point's distance proves the point can never win: skip the atomic.  In dense data (many points per cell)
+  // that removes most of the read-modify-write traffic.
+  unsigned long long seen[kPPT];
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    seen[j] = 0ull;
+    if (live[j]) seen[j] = __ldcg(g.table + slot[j]);
+  }
+  bool want[kPPT];
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    want[j] = false;
+    if (live[j] && e[j].dist_bits <= seen[j]) {
+      const unsigned long long old = atomicMin(g.table + slot[j], e[j].dist_bits);
+      want[j] = e[j].dist_bits <= old;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPPT; ++j) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, want[j]);
+    if (bal == 0u) continue;
+    const unsigned long long base = cand_reserve(g, ch, (uint32_t)__popc(bal));
+    if (want[j]) {
+      const unsigned long long ci = base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u));
+      if (ci < g.cand_cap) {
+        const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
+        uint32_t rgb[3];
+        src.colour(S, p0 + i, i, rgb);
+        uint32_t w[8];
+        point_words(S, h[j], rgb, w);
+        uint4* c4 = reinterpret_cast<uint4*>(g.cands + ci);
+        const unsigned long long gidx = S.scan_base + p0 + i;
+        c4[0] = make_uint4((uint32_t)e[j].key, (uint32_t)(e[j].key >> 32), (uint32_t)e[j].dist_bits, (uint32_t)(e[j].dist_bits >> 32));
+        c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
+        c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
+        c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
+      } else {
+        atomicOr(g.flags, kFlagCandOverflow);
+      }
     }
   }
 }
@@ -466,7 +534,7 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 
 template <int MODE, class Src>
 __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment& S, uint64_t tile, const Src& src,
-                                             unsigned long long& acc) {
+                                             unsigned long long& acc, LaneChunk& ch) {
   static_assert(MODE == MODE_COUNT || MODE == MODE_GRID, "select has its own kernels");
   const uint64_t p0 = (tile - S.first_tile) * (uint64_t)kTilePts;
   const uint64_t rem = S.n_points - p0;
@@ -487,11 +555,12 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment&
     for (int j = 0; j < kPPT; ++j) acc += m[j] ? 1ull : 0ull;
   } else {
     const GridDev& g = P.lanes[S.lane].grid;
-#pragma unroll
-    for (int j = 0; j < kPPT; ++j) {
-      const uint32_t i = (uint32_t)j * kBlock + tid;
-      grid_insert(g, S, src, m[j], h[j], p0 + i, i);
+    if (ch.lane != S.lane) {  // a warp's chunk belongs to one collector's arena
+      if (ch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[ch.lane].grid, ch.c);
+      ch.c = CandChunk();
+      ch.lane = S.lane;
     }
+    grid_insert_tile(g, S, src, m, h, p0, ch.c);
   }
 }
 
@@ -506,6 +575,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
   uint32_t seg_i = 0xFFFFFFFFu;
   uint32_t seg_cursor = 0;
   unsigned long long acc = 0;
+  LaneChunk lch;
   DirectSrc src;
 
   for (uint64_t iter = 0;; ++iter) {
@@ -528,13 +598,16 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
       seg_i = seg_cursor;
       __syncthreads();
     }
-    process_tile<MODE>(P, sseg, tile, src, acc);
+    process_tile<MODE>(P, sseg, tile, src, acc, lch);
   }
   if constexpr (MODE == MODE_COUNT) {
     if (seg_i != 0xFFFFFFFFu) {
       unsigned long long t = block_sum(acc, s_red);
       if (threadIdx.x == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
     }
+  }
+  if constexpr (MODE == MODE_GRID) {
+    if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
   }
 }
 
@@ -557,6 +630,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// same, with an L2 cache policy (record tiles are read once: evict_first keeps them from displacing the density table)
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -585,6 +666,10 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 
   const uint32_t tid = threadIdx.x;
   // producer state (meaningful in thread 0 only)
+  uint64_t stream_policy = 0;
+  if constexpr (MODE == MODE_GRID) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
+  }
   uint32_t prod_seg = 0;
   uint64_t prod_iter = 0;
 
@@ -604,7 +689,10 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     stage_tile[s] = tile;
     stage_seg[s] = prod_seg;
     mbar_arrive_expect_tx(&full_bar[s], bytes);
-    bulk_copy_g2s(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s]);
+    if constexpr (MODE == MODE_GRID)
+      bulk_copy_g2s_hint(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s], stream_policy);
+    else
+      bulk_copy_g2s(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s]);
   };
 
   if (tid == 0) {
@@ -621,6 +709,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 
   uint32_t seg_i = 0xFFFFFFFFu;
   unsigned long long acc = 0;
+  LaneChunk lch;
   for (uint32_t it = 0;; ++it) {
     const uint32_t s = it % STAGES;
     const uint32_t parity = (it / STAGES) & 1u;
@@ -644,7 +733,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     }
     mbar_wait(&full_bar[s], parity);
     SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
-    process_tile<MODE>(P, sseg, tile, src, acc);
+    process_tile<MODE>(P, sseg, tile, src, acc, lch);
     __syncthreads();  // every thread is done reading stage s
     if (tid == 0) produce((int)s);
   }
@@ -653,6 +742,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
       unsigned long long t = block_sum(acc, s_red);
       if (tid == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
     }
+  }
+  if constexpr (MODE == MODE_GRID) {
+    if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
   }
 }
 
@@ -1158,12 +1250,15 @@ __global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned 
     if (i < n_in) {
       const uint4* c4 = reinterpret_cast<const uint4*>(g.cands + i);
       c0 = c4[0];
+      c1 = c4[1];
       const uint64_t key = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
       const unsigned long long d = (unsigned long long)c0.z | ((unsigned long long)c0.w << 32);
-      const uint64_t slot = grid_slot(g, key, false);
-      keep = slot != ~0ull && g.table[slot] == d;
+      const unsigned long long sidx = (unsigned long long)c1.x | ((unsigned long long)c1.y << 32);
+      if (sidx != kCandEmpty) {
+        const uint64_t slot = grid_slot(g, key, false);
+        keep = slot != ~0ull && g.table[slot] == d;
+      }
       if (keep) {
-        c1 = c4[1];
         c2 = c4[2];
         c3 = c4[3];
       }
@@ -1189,6 +1284,7 @@ __global__ void k_grid_min_index(GridDev g, uint64_t n, unsigned long long* idx_
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
+    if (c.scan_idx == kCandEmpty) continue;
     const uint64_t slot = grid_slot(g, c.key, false);
     if (slot != ~0ull && g.table[slot] == c.dist_bits) atomicMin(idx_table + slot, (unsigned long long)c.scan_idx);
   }
@@ -1202,6 +1298,7 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, unsigned long long* idx_table
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
+    if (c.scan_idx == kCandEmpty) continue;
     const uint64_t slot = grid_slot(g, c.key, false);
     if (slot == ~0ull || g.table[slot] != c.dist_bits) continue;
     if (mode == 0) {
@@ -1305,7 +1402,7 @@ static int persistent_grid(const void* kfn, size_t smem, int sm_count, uint64_t 
 
 template <int R, int MODE>
 static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
-  constexpr int STAGES = ScanStages<R>::value;
+  constexpr int STAGES = MODE == MODE_GRID ? 2 : ScanStages<R>::value;
   constexpr size_t smem = (size_t)STAGES * kTilePts * R;
   static bool configured = false;
   auto kfn = k_scan_staged<R, MODE, STAGES>;

@@ -55,7 +55,7 @@ def main():
             ts.append(e0.elapsed_time(e1))
         return statistics.median(ts)
 
-    if args.only == "configs":
+    if args.only in ("configs", "c3", "c4"):
         run_configs(pcq, ctx, stream, timed, peak, args)
         return
     cases = [("las", 0), ("las", 1), ("las", 2), ("las", 3), ("last", 1), ("last", 3)]
@@ -167,7 +167,7 @@ def run_configs(pcq, ctx, stream, timed, peak, args):
         print(json.dumps(d), flush=True)
 
     # ---- C4: one navvis-shape file, 56.2 M points, format 3, S/L/XL + density 0.1 ----
-    for fma in (False, True):
+    for fma in ((False, True) if args.only != "c3" else ()):
         sp = S.navvis_spec(n_points=56_200_000, fma_sensitive=fma)
         buf = torch.empty(sp.n_points * sp.record_len + 256, dtype=torch.uint8, device="cuda:0")
         mm, desc = S.device_points(ctx, sp, buf.data_ptr())
@@ -186,11 +186,14 @@ def run_configs(pcq, ctx, stream, timed, peak, args):
                 s.search_files([df], impl, [g])
 
             ms_grid = timed(run, reps=5)
-            run()
-            ctx.synchronize()
-            t0 = time.perf_counter()
-            cells = g.point_count()
-            fin_ms = (time.perf_counter() - t0) * 1e3
+            fin = []
+            for _ in range(3):  # first finalisation allocates its scratch; report the steady state
+                run()
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                cells = g.point_count()
+                fin.append((time.perf_counter() - t0) * 1e3)
+            fin_ms = min(fin)
             bc = pcq.BufferCollector(ctx)
 
             def runb():
@@ -210,6 +213,8 @@ def run_configs(pcq, ctx, stream, timed, peak, args):
         del buf
         torch.cuda.empty_cache()
 
+    if args.only == "c4":
+        return
     # ---- C3: ca13-shape LAST, 64 files x 40.75 M points (only the three columns the path reads are resident) ----
     specs = S.ca13_specs()
     dfs, keep = [], []
