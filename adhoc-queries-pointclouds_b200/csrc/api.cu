@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <unordered_set>
 #include <vector>
 
 #include "host_logic.hpp"
@@ -49,6 +50,7 @@ struct DevBlock {
   unsigned long long out_count;   // GRID finalisation: winners emitted
   uint32_t flags;
   uint32_t pad_;
+  unsigned long long log_count;   // GRID: replay-log entries written by the last launch (affected keys, alias.cu)
 };
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -113,6 +115,19 @@ struct pcq_collector {
   uint8_t* d_final = nullptr;
   uint64_t final_cap = 0, final_n = 0;
   bool final_valid = false;
+  // key-aliasing replay (alias.cu): affected keys in ordinal order, their fold states (host copy is authoritative
+  // between launches), the device-side set and the replay log
+  std::vector<uint64_t> akeys;
+  std::vector<AliasState> astates;
+  unsigned long long* d_akeys = nullptr;
+  uint32_t* d_aord = nullptr;
+  uint64_t a_slots = 0, a_slots_cap = 0;
+  AliasState* d_astates = nullptr;
+  uint64_t d_astates_cap = 0;
+  Candidate* d_log = nullptr;
+  uint64_t log_cap = 0;
+  uint64_t scan_hi = 0;       // end of the highest point range fed so far: the replay needs launches in scan order
+  uint64_t prune_epoch = 0;   // bumped whenever candidates are dropped (prune / rehash)
   // export scratch
   Candidate* d_export = nullptr;
   uint64_t export_cap = 0;
@@ -284,7 +299,80 @@ GridDev grid_view(const pcq_collector* c) {
   GridDev g = c->grid;
   g.cand_count = &c->dev->cand_count;
   g.flags = &c->dev->flags;
+  g.alias_keys = c->a_slots ? c->d_akeys : nullptr;
+  g.alias_ord = c->a_slots ? c->d_aord : nullptr;
+  g.alias_slots = c->a_slots;
+  g.log_only = 0;
+  g.log = c->d_log;
+  g.log_count = &c->dev->log_count;
+  g.log_cap = c->log_cap;
   return g;
+}
+
+int grow_log(pcq_collector* c, uint64_t need) {
+  if (c->log_cap >= need) return PCQ_OK;
+  CU(cudaStreamSynchronize(c->ctx->stream));
+  if (c->d_log) cudaFree(c->d_log);
+  c->d_log = nullptr;
+  c->log_cap = 0;
+  const uint64_t cap = std::max<uint64_t>(need, 1u << 14);
+  if (cudaMalloc(&c->d_log, cap * sizeof(Candidate)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_NOMEM, "cannot allocate a replay log of %llu entries", (unsigned long long)cap);
+  }
+  c->log_cap = cap;
+  return PCQ_OK;
+}
+
+// (re)build the device-side set of affected keys and upload the host copy of their states
+int alias_upload(pcq_collector* c) {
+  pcq_ctx* ctx = c->ctx;
+  const uint64_t n = c->akeys.size();
+  if (n == 0) {
+    c->a_slots = 0;
+    return PCQ_OK;
+  }
+  uint64_t slots = 64;
+  while (slots < 4 * n) slots <<= 1;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (c->a_slots_cap < slots) {
+    if (c->d_akeys) cudaFree(c->d_akeys);
+    if (c->d_aord) cudaFree(c->d_aord);
+    c->d_akeys = nullptr;
+    c->d_aord = nullptr;
+    c->a_slots_cap = 0;
+    CU(cudaMalloc(&c->d_akeys, slots * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_aord, slots * sizeof(uint32_t)));
+    c->a_slots_cap = slots;
+  }
+  if (c->d_astates_cap < n) {
+    if (c->d_astates) cudaFree(c->d_astates);
+    c->d_astates = nullptr;
+    c->d_astates_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(2 * n, 256);
+    CU(cudaMalloc(&c->d_astates, cap * sizeof(AliasState)));
+    c->d_astates_cap = cap;
+  }
+  std::vector<unsigned long long> hk(slots, ~0ull);
+  std::vector<uint32_t> ho(slots, 0u);
+  const uint64_t mask = slots - 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t x = c->akeys[i];  // mix64 of kernels.cu
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    uint64_t s = x & mask;
+    while (hk[s] != ~0ull) s = (s + 1) & mask;
+    hk[s] = c->akeys[i];
+    ho[s] = (uint32_t)i;
+  }
+  CU(cudaMemcpy(c->d_akeys, hk.data(), slots * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_aord, ho.data(), slots * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_astates, c->astates.data(), n * sizeof(AliasState), cudaMemcpyHostToDevice));
+  c->a_slots = slots;
+  return PCQ_OK;
 }
 
 int grow_cands(pcq_collector* c, uint64_t need) {
@@ -306,6 +394,7 @@ int grow_cands(pcq_collector* c, uint64_t need) {
 // drop candidates that no longer hold their cell's minimum; compacts in place through a scratch arena
 int prune_cands(pcq_collector* c) {
   pcq_ctx* ctx = c->ctx;
+  c->prune_epoch++;
   if (c->cand_len == 0) return PCQ_OK;
   Candidate* tmp = nullptr;
   CU(cudaMalloc(&tmp, std::max<uint64_t>(c->cand_len, 1) * sizeof(Candidate)));
@@ -395,41 +484,145 @@ int grid_finalize(pcq_collector* c) {
   if (c->final_valid) return PCQ_OK;
   pcq_ctx* ctx = c->ctx;
   const uint64_t n = c->cand_len;
+  // winners of affected keys come from the ordered replay, not from the table
+  std::vector<uint8_t> replayed;
+  for (const AliasState& s : c->astates)
+    if (s.valid) replayed.insert(replayed.end(), s.point, s.point + 31);
+  const uint64_t n_replayed = replayed.size() / 31;
   c->final_n = 0;
-  if (n == 0) {
+  if (n == 0 && n_replayed == 0) {
     c->final_valid = true;
     return PCQ_OK;
   }
-  if (ctx->idx_scratch_cap < c->grid.table_slots) {
-    if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
-    ctx->idx_scratch = nullptr;
-    ctx->idx_scratch_cap = 0;
-    if (cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(PCQ_ERR_NOMEM, "cannot allocate density index table");
-    }
-    ctx->idx_scratch_cap = c->grid.table_slots;
-  }
-  CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
-  if (c->final_cap < n) {
+  if (c->final_cap < n + n_replayed) {
     if (c->d_final) cudaFree(c->d_final);
     c->d_final = nullptr;
     c->final_cap = 0;
-    CU(cudaMalloc(&c->d_final, n * 31ull + 64));
-    c->final_cap = n;
+    CU(cudaMalloc(&c->d_final, (n + n_replayed) * 31ull + 64));
+    c->final_cap = n + n_replayed;
   }
-  CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
-  GridDev g = grid_view(c);
-  if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0)
-    return fail(PCQ_ERR_CUDA, "k_grid_min_index launch failed");
-  if (launch_grid_emit(g, n, ctx->idx_scratch, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count,
-                       ctx->sm_count, ctx->stream) != 0)
-    return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
-  ctx->launches += 2;
-  DevBlock b;
-  RC(read_devblock(c, &b));
-  c->final_n = b.out_count;
+  uint64_t from_table = 0;
+  if (n) {
+    if (ctx->idx_scratch_cap < c->grid.table_slots) {
+      if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
+      ctx->idx_scratch = nullptr;
+      ctx->idx_scratch_cap = 0;
+      if (cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PCQ_ERR_NOMEM, "cannot allocate density index table");
+      }
+      ctx->idx_scratch_cap = c->grid.table_slots;
+    }
+    CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+    CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
+    GridDev g = grid_view(c);
+    if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0)
+      return fail(PCQ_ERR_CUDA, "k_grid_min_index launch failed");
+    if (launch_grid_emit(g, n, ctx->idx_scratch, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count,
+                         ctx->sm_count, ctx->stream) != 0)
+      return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
+    ctx->launches += 2;
+    DevBlock b;
+    RC(read_devblock(c, &b));
+    from_table = b.out_count;
+  }
+  if (n_replayed) {
+    CU(cudaMemcpyAsync(c->d_final + from_table * 31ull, replayed.data(), replayed.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  c->final_n = from_table + n_replayed;
   c->final_valid = true;
+  return PCQ_OK;
+}
+
+// A GRID launch logged points of affected keys (key aliasing, see alias.cu).  New affected keys get their fold state
+// from the earlier launches, a second (log-only) pass collects every point of theirs in this launch, and the log is
+// replayed in scan order.
+int alias_slow_path(pcq_ctx* ctx, const std::vector<Segment>& segs, ScanParams P, int variant, uint32_t R, int min_align,
+                    pcq_collector* const* collectors, uint32_t n_collectors, std::vector<DevBlock>& blocks,
+                    const std::vector<uint64_t>& epoch0, const std::vector<uint64_t>& lane_lo) {
+  bool pass2 = false;
+  for (uint32_t l = 0; l < n_collectors; ++l) {
+    pcq_collector* c = collectors[l];
+    const uint64_t n_log = blocks[l].log_count;
+    if (n_log == 0) continue;
+    std::vector<Candidate> h(n_log);
+    CU(cudaMemcpy(h.data(), c->d_log, n_log * sizeof(Candidate), cudaMemcpyDeviceToHost));
+    std::unordered_set<uint64_t> known(c->akeys.begin(), c->akeys.end());
+    std::vector<uint64_t> fresh;
+    for (const Candidate& e : h)
+      if (known.insert(e.key).second) fresh.push_back(e.key);
+    if (fresh.empty()) continue;
+    if (lane_lo[l] < c->scan_hi)
+      return fail(PCQ_ERR_ALIASED,
+                  "density grid: key aliasing (grid_sampling.rs:62-70 vs 78-82) makes the result depend on insertion order; "
+                  "the ordered replay needs point ranges fed in scan order, but this launch starts at scan index %llu "
+                  "after %llu was already fed",
+                  (unsigned long long)lane_lo[l], (unsigned long long)c->scan_hi);
+    if (c->prune_epoch != epoch0[l])
+      return fail(PCQ_ERR_ALIASED,
+                  "density grid: key aliasing met in a launch that also had to drop candidates (table rehash / arena "
+                  "overflow); the earlier winner of the aliased key is no longer available for the ordered replay");
+    const uint32_t ord0 = (uint32_t)c->akeys.size();
+    c->akeys.insert(c->akeys.end(), fresh.begin(), fresh.end());
+    c->astates.resize(c->akeys.size());
+    for (size_t k = ord0; k < c->astates.size(); ++k) std::memset(&c->astates[k], 0, sizeof(AliasState));
+    RC(alias_upload(c));
+    GridDev g = grid_view(c);
+    if (alias_prewinners(g, c->cand_len, nullptr, (uint32_t)fresh.size(), lane_lo[l], c->d_astates, ord0, ctx->sm_count,
+                         ctx->stream) != 0)
+      return fail(PCQ_ERR_CUDA, "alias_prewinners failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += 3;
+    CU(cudaMemcpy(c->astates.data() + ord0, c->d_astates + ord0, fresh.size() * sizeof(AliasState), cudaMemcpyDeviceToHost));
+    pass2 = true;
+  }
+  if (pass2) {
+    // the first pass could not know the new keys: collect every point of an affected key again, insert nothing
+    bool done = false;
+    for (int attempt = 0; attempt < 8 && !done; ++attempt) {
+      std::vector<LaneDev> lanes(n_collectors);
+      for (uint32_t l = 0; l < n_collectors; ++l) {
+        pcq_collector* c = collectors[l];
+        CU(cudaMemsetAsync(&c->dev->log_count, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(&c->dev->flags, 0, sizeof(uint32_t), ctx->stream));
+        std::memset(&lanes[l], 0, sizeof(LaneDev));
+        lanes[l].count = &c->dev->count;
+        lanes[l].grid = grid_view(c);
+        lanes[l].grid.log_only = 1;
+      }
+      void* d_segs = nullptr;
+      void* d_lanes = nullptr;
+      RC(upload(ctx, segs.data(), segs.size() * sizeof(Segment), &d_segs));
+      RC(upload(ctx, lanes.data(), lanes.size() * sizeof(LaneDev), &d_lanes));
+      P.segs = static_cast<const Segment*>(d_segs);
+      P.lanes = static_cast<const LaneDev*>(d_lanes);
+      if (launch_scan(variant, MODE_GRID, P, R, min_align, ctx->sm_count, ctx->stream) != 0)
+        return fail(PCQ_ERR_CUDA, "scan kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      ctx->launches++;
+      for (uint32_t l = 0; l < n_collectors; ++l)
+        CU(cudaMemcpyAsync(&blocks[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      done = true;
+      for (uint32_t l = 0; l < n_collectors; ++l) {
+        if (blocks[l].flags & kFlagLogOverflow) {
+          RC(grow_log(collectors[l], blocks[l].log_count + blocks[l].log_count / 4 + 1024));
+          done = false;
+        }
+      }
+    }
+    if (!done) return fail(PCQ_ERR_NOMEM, "replay log capacity did not converge");
+  }
+  for (uint32_t l = 0; l < n_collectors; ++l) {
+    pcq_collector* c = collectors[l];
+    const uint64_t n_log = blocks[l].log_count;
+    if (n_log == 0) continue;
+    GridDev g = grid_view(c);
+    const int rc = alias_replay(g, n_log, c->d_astates, ctx->sm_count, ctx->stream);
+    if (rc != 0) return fail(rc == -2 ? PCQ_ERR_NOMEM : PCQ_ERR_CUDA, "alias replay of %llu points failed", (unsigned long long)n_log);
+    ctx->launches += 5;
+    CU(cudaMemcpy(c->astates.data(), c->d_astates, c->astates.size() * sizeof(AliasState), cudaMemcpyDeviceToHost));
+    c->final_valid = false;
+  }
   return PCQ_OK;
 }
 
@@ -484,10 +677,24 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       if (lane_points[l] == 0) continue;
-      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16);
+      const uint64_t slack = (uint64_t)ctx->sm_count * kGridCtasPerSm * (kBlock / 32) * kCandChunk;
+      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16) + slack;
+      // Candidates are only ever dropped BETWEEN launches: what survives is every cell's current winner, which is
+      // exactly what a later launch needs if one of its points makes the cell's key an aliased one (alias.cu).
+      if (c->cand_len + guess > c->grid.cand_cap && c->cand_len > (1u << 20)) RC(prune_cands(c));
       RC(grow_cands(c, c->cand_len + guess));
+      RC(grow_log(c, 1u << 14));
       c->final_valid = false;
     }
+  }
+  // GRID: scan-index range of every lane in this launch and the prune epochs (ordered alias replay, alias.cu)
+  std::vector<uint64_t> lane_lo(n_collectors, ~0ull), lane_hi(n_collectors, 0), epoch0(n_collectors, 0);
+  if (kind == PCQ_COLLECT_GRID) {
+    for (const Segment& s : segs) {
+      lane_lo[s.lane] = std::min<uint64_t>(lane_lo[s.lane], s.scan_base);
+      lane_hi[s.lane] = std::max<uint64_t>(lane_hi[s.lane], s.scan_base + s.n_points);
+    }
+    for (uint32_t l = 0; l < n_collectors; ++l) epoch0[l] = collectors[l]->prune_epoch;
   }
 
   for (int attempt = 0; attempt < 8; ++attempt) {
@@ -563,29 +770,46 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       const DevBlock& b = blocks[l];
-      if (b.flags & kFlagAliased)
-        return fail(PCQ_ERR_ALIASED,
-                    "density grid: a matching point falls into a cell index above its bit mask; the reference's result "
-                    "for the aliased key depends on insertion order (grid_sampling.rs:62-70 vs 78-82)");
       if (b.flags & kFlagHashFull) {
         RC(rehash_grid(c));
         retry = true;
         continue;
       }
       if (b.flags & kFlagCandOverflow) {
+        // Rewind to the candidates of the earlier launches and run the launch again into a larger arena.  (The table
+        // keeps what the failed attempt wrote: a cell's true winner still qualifies, non-winners no longer do.)
         const uint64_t attempted = b.cand_count;  // what this launch wanted in total
-        const uint64_t before = c->cand_len;
-        c->cand_len = c->grid.cand_cap;           // the arena is full of valid candidates
-        RC(prune_cands(c));
-        RC(grow_cands(c, c->cand_len + (attempted - before) + (attempted - before) / 4 + 1024));
+        RC(grow_cands(c, attempted + attempted / 4 + (uint64_t)ctx->sm_count * kGridCtasPerSm * (kBlock / 32) * kCandChunk));
+        const unsigned long long keep = c->cand_len;
+        CU(cudaMemcpyAsync(&c->dev->cand_count, &keep, sizeof(keep), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemsetAsync(&c->dev->flags, 0, sizeof(uint32_t), ctx->stream));
+        retry = true;
+        continue;
+      }
+      if (b.flags & kFlagLogOverflow) {
+        RC(grow_log(c, b.log_count + b.log_count / 4 + 1024));
         CU(cudaMemsetAsync(&c->dev->flags, 0, sizeof(uint32_t), ctx->stream));
         retry = true;
         continue;
       }
       c->cand_len = b.cand_count;
     }
-    if (!retry) return PCQ_OK;
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (retry) {
+      for (uint32_t l = 0; l < n_collectors; ++l)
+        CU(cudaMemsetAsync(&collectors[l]->dev->log_count, 0, sizeof(unsigned long long), ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      continue;
+    }
+    bool any_logged = false;
+    for (uint32_t l = 0; l < n_collectors; ++l) any_logged |= blocks[l].log_count != 0;
+    if (any_logged) RC(alias_slow_path(ctx, segs, P, variant, R, min_align, collectors, n_collectors, blocks, epoch0, lane_lo));
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      if (lane_hi[l] > c->scan_hi) c->scan_hi = lane_hi[l];
+      CU(cudaMemsetAsync(&c->dev->log_count, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    return PCQ_OK;
   }
   return fail(PCQ_ERR_NOMEM, "collector capacity did not converge");
 }
@@ -884,6 +1108,10 @@ void pcq_collector_destroy(pcq_collector* c) {
   if (c->grid.cands) cudaFree(c->grid.cands);
   if (c->d_final) cudaFree(c->d_final);
   if (c->d_export) cudaFree(c->d_export);
+  if (c->d_akeys) cudaFree(c->d_akeys);
+  if (c->d_aord) cudaFree(c->d_aord);
+  if (c->d_astates) cudaFree(c->d_astates);
+  if (c->d_log) cudaFree(c->d_log);
   if (c->h_pts) cudaFreeHost(c->h_pts);
   ctx_unref(c->ctx);
   delete c;
@@ -899,6 +1127,10 @@ int pcq_collector_reset(pcq_collector* c) {
   c->cand_len = 0;
   c->final_valid = false;
   c->final_n = 0;
+  c->akeys.clear();
+  c->astates.clear();
+  c->a_slots = 0;
+  c->scan_hi = 0;
   if (c->kind == PCQ_COLLECT_GRID) {
     CU(cudaMemsetAsync(c->grid.table, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
     if (c->grid.hkeys) CU(cudaMemsetAsync(c->grid.hkeys, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
@@ -1198,6 +1430,11 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
   RC(use_device(ctx));
   *out_dev_candidates = nullptr;
   for (uint32_t p = 0; p < n_parts; ++p) counts[p] = 0;
+  if (!c->akeys.empty())
+    return fail(PCQ_ERR_ALIASED,
+                "density grid: %zu cell keys suffer key aliasing (grid_sampling.rs:62-70 vs 78-82); their result is a "
+                "sequential fold in scan order, which cannot be merged across GPUs",
+                c->akeys.size());
   const uint64_t n = c->cand_len;
   if (n == 0) return PCQ_OK;
   if (ctx->idx_scratch_cap < c->grid.table_slots) {

@@ -27,6 +27,7 @@
 #include <cstdint>
 
 #include "pcq_device.h"
+#include "grid_math.cuh"
 
 namespace pcq {
 
@@ -44,22 +45,6 @@ __device__ __forceinline__ bool in_range(int32_t v, int32_t lo, int32_t hi) {
 // (v as f64 * scale) + offset, las.rs:139-141 — two roundings, never an FMA
 __device__ __forceinline__ double reconstruct(int32_t v, double scale, double offset) {
   return __dadd_rn(__dmul_rn((double)v, scale), offset);
-}
-
-// Rust `f64 as u64`: NaN -> 0, negative -> 0, saturating (grid_sampling.rs:58-60)
-__device__ __forceinline__ uint64_t f64_as_u64(double v) {
-  if (!(v > 0.0)) return 0ull;  // NaN, -x, +-0
-  if (v >= 18446744073709551616.0) return ~0ull;
-  return (uint64_t)v;  // truncates toward zero
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return x;
 }
 
 // global loads of possibly unaligned little-endian fields
@@ -362,47 +347,10 @@ __device__ __forceinline__ uint64_t grid_slot(const GridDev& g, uint64_t key, bo
   return ~0ull;
 }
 
-struct CellEval {
-  uint64_t key;
-  unsigned long long dist_bits;
-  bool aliased;
-};
-
-__device__ __forceinline__ CellEval grid_eval(const GridDev& g, double px, double py, double pz) {
-  // :51-56  r = (p - min) * dims as f64 / (max - min);  :58-60  cell = r as u64
-  // A zero numerator (a point exactly on a minimum face — common on synthetic and on clipped data) sends the
-  // whole warp through the slow path of the IEEE division; 0 / d is 0 or NaN and both cast to cell 0, so such
-  // lanes divide 1.0 instead and ignore the quotient.
-  const double nx = __dmul_rn(__dsub_rn(px, g.bmin[0]), g.dims_f[0]);
-  const double ny = __dmul_rn(__dsub_rn(py, g.bmin[1]), g.dims_f[1]);
-  const double nz = __dmul_rn(__dsub_rn(pz, g.bmin[2]), g.dims_f[2]);
-  const double rx = __ddiv_rn(nx == 0.0 ? 1.0 : nx, __dsub_rn(g.bmax[0], g.bmin[0]));
-  const double ry = __ddiv_rn(ny == 0.0 ? 1.0 : ny, __dsub_rn(g.bmax[1], g.bmin[1]));
-  const double rz = __ddiv_rn(nz == 0.0 ? 1.0 : nz, __dsub_rn(g.bmax[2], g.bmin[2]));
-  const uint64_t cx = nx == 0.0 ? 0ull : f64_as_u64(rx);
-  const uint64_t cy = ny == 0.0 ? 0ull : f64_as_u64(ry);
-  const uint64_t cz = nz == 0.0 ? 0ull : f64_as_u64(rz);
-  CellEval e;
-  // a cell above its mask aliases a low cell while its centre lies elsewhere (:62-70 vs :78-82)
-  e.aliased = (cx > g.mask[0]) | (cy > g.mask[1]) | (cz > g.mask[2]);
-  e.key = (cx & g.mask[0]) | ((cy & g.mask[1]) << g.shift_y) | ((cz & g.mask[2]) << g.shift_z);
-  // :78-82  centre = (cell as f64 + 0.5) * cell_size + min   (unmasked cell)
-  double ccx = __dadd_rn(__dmul_rn(__dadd_rn(__ull2double_rn(cx), 0.5), g.cell_size), g.bmin[0]);
-  double ccy = __dadd_rn(__dmul_rn(__dadd_rn(__ull2double_rn(cy), 0.5), g.cell_size), g.bmin[1]);
-  double ccz = __dadd_rn(__dmul_rn(__dadd_rn(__ull2double_rn(cz), 0.5), g.cell_size), g.bmin[2]);
-  // :84-95  distance_squared = (dx*dx + dy*dy) + dz*dz  (nalgebra 0.23, no FMA)
-  double dx = __dsub_rn(ccx, px), dy = __dsub_rn(ccy, py), dz = __dsub_rn(ccz, pz);
-  double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-  e.dist_bits = (unsigned long long)__double_as_longlong(d);  // d >= +0: bit order == value order
-  return e;
-}
-
 // Candidate arena allocation.  One global counter bumped once per warp and append serialises on its L2 atomic
 // unit (it was a quarter of the insert kernel's time); instead every warp owns a private chunk of kCandChunk
-// slots, fills it without any atomic and takes a new chunk with ONE atomicAdd when it is full.  Slots a warp
+// (pcq_device.h) slots, fills it without any atomic and takes a new chunk with ONE atomicAdd when it is full.  Slots a warp
 // reserved but did not use are marked empty (scan_idx == ~0) and skipped by every consumer of the arena.
-constexpr uint32_t kCandChunk = 128;
-constexpr unsigned long long kCandEmpty = ~0ull;
 
 struct CandChunk {
   unsigned long long base = 0;
@@ -462,9 +410,25 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
       const double py = reconstruct(h[j].y, S.scale[1], S.offset[1]);
       const double pz = reconstruct(h[j].z, S.scale[2], S.offset[2]);
       e[j] = grid_eval(g, px, py, pz);
-      if (e[j].aliased) {
-        atomicOr(g.flags, kFlagAliased);
-      } else {
+      if (e[j].aliased || alias_find(g, e[j].key) != ~0u) {
+        // a point of an affected key: logged for the ordered replay, never enters the table (rare path)
+        const unsigned long long li = atomicAdd(g.log_count, 1ull);
+        if (li < g.log_cap) {
+          const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
+          uint32_t rgb[3];
+          src.colour(S, p0 + i, i, rgb);
+          uint32_t w[8];
+          point_words(S, h[j], rgb, w);
+          uint4* c4 = reinterpret_cast<uint4*>(g.log + li);
+          const unsigned long long gidx = S.scan_base + p0 + i;
+          c4[0] = make_uint4((uint32_t)e[j].key, (uint32_t)(e[j].key >> 32), 0u, 0u);
+          c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
+          c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
+          c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
+        } else {
+          atomicOr(g.flags, kFlagLogOverflow);
+        }
+      } else if (!g.log_only) {
         slot[j] = grid_slot(g, e[j].key, true);
         if (slot[j] == ~0ull)
           atomicOr(g.flags, kFlagHashFull);
@@ -1254,7 +1218,7 @@ __global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned 
       const uint64_t key = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
       const unsigned long long d = (unsigned long long)c0.z | ((unsigned long long)c0.w << 32);
       const unsigned long long sidx = (unsigned long long)c1.x | ((unsigned long long)c1.y << 32);
-      if (sidx != kCandEmpty) {
+      if (sidx != kCandEmpty && alias_find(g, key) == ~0u) {  // candidates of affected keys are dead weight
         const uint64_t slot = grid_slot(g, key, false);
         keep = slot != ~0ull && g.table[slot] == d;
       }
@@ -1284,7 +1248,7 @@ __global__ void k_grid_min_index(GridDev g, uint64_t n, unsigned long long* idx_
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
-    if (c.scan_idx == kCandEmpty) continue;
+    if (c.scan_idx == kCandEmpty || alias_find(g, c.key) != ~0u) continue;  // affected keys come from the replay
     const uint64_t slot = grid_slot(g, c.key, false);
     if (slot != ~0ull && g.table[slot] == c.dist_bits) atomicMin(idx_table + slot, (unsigned long long)c.scan_idx);
   }
@@ -1298,7 +1262,7 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, unsigned long long* idx_table
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
-    if (c.scan_idx == kCandEmpty) continue;
+    if (c.scan_idx == kCandEmpty || alias_find(g, c.key) != ~0u) continue;
     const uint64_t slot = grid_slot(g, c.key, false);
     if (slot == ~0ull || g.table[slot] != c.dist_bits) continue;
     if (mode == 0) {
@@ -1411,7 +1375,7 @@ static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
     configured = true;
   }
   unsigned grid = 0;
-  if (persistent_grid((const void*)kfn, smem, sm_count, p.n_tiles, 4, &grid) != 0) return -1;
+  if (persistent_grid((const void*)kfn, smem, sm_count, p.n_tiles, (int)kGridCtasPerSm, &grid) != 0) return -1;
   if (grid == 0) return 0;
   kfn<<<grid, kBlock, smem, st>>>(p);
   return check_launch();
@@ -1433,7 +1397,7 @@ template <int MODE>
 static int launch_direct_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   auto kfn = k_scan_direct<MODE>;
   unsigned grid = 0;
-  if (persistent_grid((const void*)kfn, 0, sm_count, p.n_tiles, 8, &grid) != 0) return -1;
+  if (persistent_grid((const void*)kfn, 0, sm_count, p.n_tiles, MODE == MODE_GRID ? (int)kGridCtasPerSm : 8, &grid) != 0) return -1;
   if (grid == 0) return 0;
   kfn<<<grid, kBlock, 0, st>>>(p);
   return check_launch();

@@ -66,12 +66,37 @@ struct GridDev {
   Candidate* cands;
   unsigned long long* cand_count;
   uint64_t cand_cap;
-  uint32_t* flags;      // bit 0: aliased key seen, bit 1: candidate arena overflow, bit 2: hash full
+  uint32_t* flags;      // bit 0: (unused), bit 1: candidate arena overflow, bit 2: hash full, bit 3: replay log overflow
+  // Key aliasing (grid_sampling.rs:62-70 vs 78-82): a point whose cell index exceeds its bit mask on some axis shares
+  // the key of a low cell while its centre lies elsewhere, which makes the reference's fold for that key depend on
+  // insertion order.  Such keys are "affected": their points bypass the atomic-min table, are logged, and are
+  // replayed in scan order (k_alias_fold).  alias_keys is an open-addressing set of affected keys (~0 = empty),
+  // alias_ord[slot] the ordinal of the key in the collector's state array.
+  const unsigned long long* alias_keys;
+  const uint32_t* alias_ord;
+  uint64_t alias_slots;  // power of two, 0 when no key is affected yet
+  uint32_t log_only;     // 1: second pass of a launch that met new affected keys — log their points, insert nothing
+  uint32_t pad_;
+  Candidate* log;        // replay log: {key, -, scan index, point} of every point of an affected key / aliased point
+  unsigned long long* log_count;
+  uint64_t log_cap;
 };
 
-constexpr uint32_t kFlagAliased = 1u;
+// candidates are appended through warp-private chunks of this many arena slots (kernels.cu); a launch can leave up
+// to one partly used chunk per warp and lane behind, which the host adds to every capacity estimate
+constexpr uint32_t kCandChunk = 64;
+constexpr uint32_t kGridCtasPerSm = 4;  // upper bound of resident scan CTAs per SM in grid mode
+
 constexpr uint32_t kFlagCandOverflow = 2u;
 constexpr uint32_t kFlagHashFull = 4u;
+constexpr uint32_t kFlagLogOverflow = 8u;
+
+// state of one affected key: what SparseGrid's HashMap holds for it after the points replayed so far
+struct AliasState {
+  uint8_t point[31];
+  uint8_t valid;
+};
+static_assert(sizeof(AliasState) == 32, "alias state must be 32 bytes");
 
 // Per-lane (per-collector) device state for one launch.
 struct LaneDev {
@@ -109,5 +134,13 @@ int launch_grid_emit(const GridDev& g, uint64_t n, unsigned long long* idx_table
                      unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
                      uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream);
 int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream);
+
+// alias replay (alias.cu).  All asynchronous on `stream` unless stated otherwise.
+// best earlier candidate (scan index < before_scan) of each key listed in `keys` -> states[ord0 + i]
+int alias_prewinners(const GridDev& g, uint64_t n_cands, const unsigned long long* d_keys, uint32_t n_keys,
+                     unsigned long long before_scan, AliasState* d_states, uint32_t ord0, int sm_count, void* stream);
+// sort the first n log entries by (key, scan index) and fold them into the states, one affected key per thread;
+// synchronises the stream (temporary storage is freed before returning)
+int alias_replay(const GridDev& g, uint64_t n, AliasState* d_states, int sm_count, void* stream);
 
 }  // namespace pcq

@@ -325,13 +325,93 @@ def test_density_hashed_table(pcq, ctx):
         del os.environ["PCQ_DENSE_MAX_BITS"], os.environ["PCQ_HASH_SLOTS_LOG2"]
 
 
-def test_density_aliasing_is_detected(pcq, ctx):
-    # KAV-6: doc-S grid has 8 z-cells (3 bits); z = 200.00 lies on the inclusive max face -> cell 8 -> masked to 0
-    xyz = np.array([[1000, 1000, 500], [1100, 1100, 20000], [1200, 1200, 1200]], np.int32)
-    f = make_file(xyz, [2, 2, 2], fmt=1, scale=(0.01,) * 3, offset=(390000.0, 130000.0, 0.0))
+def test_density_aliasing_kav6_all_orders(pcq, ctx):
+    """KAV-6: doc-S grid has 8 z-cells (3 bits); z = 200.00 lies on the inclusive max face -> cell 8 -> masked to 0,
+    so A, B, C share key 0 while B is measured against another centre: the reference's result depends on insertion
+    order (grid_sampling.rs:62-70 vs 78-82).  The ordered replay must reproduce every order's winner."""
+    import itertools
+    import json
+    from pathlib import Path
+
+    kav = json.loads((Path(__file__).parent / "golden" / "kav.json").read_text())["alias_order"]
+    pts = {"A": [1000, 1000, 500], "B": [1100, 1100, 20000], "C": [1200, 1200, 1200]}
     qmin, qmax = pcq.synth.DOC_S
+    for order in itertools.permutations("ABC"):
+        xyz = np.array([pts[k] for k in order], np.int32)
+        f = make_file(xyz, [2, 2, 2], fmt=1, scale=(0.01,) * 3, offset=(390000.0, 130000.0, 0.0))
+        want = oracle_run([f], ["las"], orc.COLLECT_GRID, bounds=(qmin, qmax), grid=(qmin, qmax, 25.0))
+        got = gpu_run(pcq, ctx, [f], ["las"], orc.COLLECT_GRID, bounds=(qmin, qmax), grid=(qmin, qmax, 25.0))
+        assert_same(orc.COLLECT_GRID, got, want)
+        winner = kav["winners"]["".join(order)]
+        assert got[0].points()["pos"][0].tolist() == [float(v) for v in kav[winner]]
+
+
+def _alias_files(rng, n_files, n, layout="las", fmt=1):
+    """points of a 128 x 128 x 8-cell grid (16 x 16 x 1 at cell 0.125: power-of-two dims on every axis); a tenth of
+    them sit exactly on a max face (raw 16384 / 1024 at scale 2^-10), where the cell index exceeds its mask"""
+    files = []
+    for _ in range(n_files):
+        xyz = rng.integers(0, 16_384, size=(n, 3), dtype=np.int32)
+        xyz[:, 2] = rng.integers(0, 1025, size=n)
+        face = rng.random(n) < 0.1
+        axis = rng.integers(0, 3, size=n)
+        for a, top in ((0, 16_384), (1, 16_384), (2, 1024)):
+            xyz[face & (axis == a), a] = top
+        cls = rng.choice(np.array([2, 2, 6], np.uint8), size=n)
+        files.append(make_file(xyz, cls, fmt=fmt, scale=(2.0 ** -10,) * 3, offset=(0.0, 0.0, 0.0), layout=layout,
+                               seed=int(rng.integers(1 << 30))))
+    return files
+
+
+ALIAS_BOX = ([0.0, 0.0, 0.0], [16.0, 16.0, 1.0])
+ALIAS_CELL = 0.125
+
+
+@pytest.mark.parametrize("layout,fmt", [("las", 1), ("las", 3), ("last", 2)])
+def test_density_aliasing_replay_matches_reference_fold(pcq, ctx, layout, fmt):
+    rng = np.random.default_rng(7 + fmt)
+    files = _alias_files(rng, 3, 20_000, layout, fmt)
+    exts = [layout] * 3
+    grid = (ALIAS_BOX[0], ALIAS_BOX[1], ALIAS_CELL)
+    assert orc.Grid(*grid).dims_bits() == ([128, 128, 8], [7, 7, 3])
+    # one collector over all files in one call, one collector per file, and file after file into one collector
+    for per_file in (False, True):
+        want = oracle_run(files, exts, orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid, per_file=per_file)
+        got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid, per_file=per_file)
+        assert_same(orc.COLLECT_GRID, got, want)
+    want = oracle_run(files, exts, orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid)
+    g = pcq.GridSampledCollector(*grid, ctx=ctx)
+    s = pcq.BoundsSearcher(*ALIAS_BOX)
+    for f in files:
+        s.search_file((f, layout), _impl(pcq), g)
+    assert_same(orc.COLLECT_GRID, [g], want)
+    # class query: every point of the class is a match, the grid is the query-independent box (main.rs:253-264)
+    want = oracle_run(files, exts, orc.COLLECT_GRID, cls=2, grid=grid)
+    got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_GRID, cls=2, grid=grid)
+    assert_same(orc.COLLECT_GRID, got, want)
+
+
+def test_density_aliasing_replay_host_streamed_chunks(pcq, ctx):
+    """host-staged search: every 1 MB chunk is its own launch, so affected keys appear launch after launch"""
+    rng = np.random.default_rng(17)
+    files = _alias_files(rng, 2, 150_000)
+    grid = (ALIAS_BOX[0], ALIAS_BOX[1], ALIAS_CELL)
+    want = oracle_run(files, ["las"] * 2, orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid)
+    os.environ["PCQ_CHUNK_MB"] = "1"
+    try:
+        got = gpu_run(pcq, ctx, files, ["las"] * 2, orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid, host_stream=True)
+    finally:
+        del os.environ["PCQ_CHUNK_MB"]
+    assert_same(orc.COLLECT_GRID, got, want)
+
+
+def test_density_aliasing_refuses_cross_gpu_merge(pcq, ctx):
+    rng = np.random.default_rng(3)
+    files = _alias_files(rng, 1, 5_000)
+    grid = (ALIAS_BOX[0], ALIAS_BOX[1], ALIAS_CELL)
+    got = gpu_run(pcq, ctx, files, ["las"], orc.COLLECT_GRID, bounds=ALIAS_BOX, grid=grid)
     with pytest.raises(pcq.PcqError) as e:
-        gpu_run(pcq, ctx, [f], ["las"], orc.COLLECT_GRID, bounds=(qmin, qmax), grid=(qmin, qmax, 25.0))
+        got[0].export_candidates(2)
     assert e.value.code == pcq.binding.PCQ_ERR_ALIASED
 
 
