@@ -618,9 +618,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-template <int R, int MODE, int STAGES>
+// LAST positions (12-byte records) in count mode: 1024-record tiles, each thread takes 4 consecutive records with
+// three conflict-free 16-byte shared loads — a quarter of the load instructions of the generic path, which is what
+// a 12-byte-per-point scan needs to stay memory- rather than issue-bound.
+constexpr int kTilePtsPos = 1024;
+
+template <int R, int MODE, int STAGES, int TP = kTilePts>
 __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
-  constexpr uint32_t kTileBytes = (uint32_t)kTilePts * (uint32_t)R;
+  constexpr uint32_t kTileBytes = (uint32_t)TP * (uint32_t)R;
   extern __shared__ __align__(128) uint8_t dsm[];  // STAGES * kTileBytes
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ unsigned long long stage_tile[STAGES];
@@ -646,9 +651,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     }
     while (prod_seg + 1 < P.n_segs && tile >= P.segs[prod_seg + 1].first_tile) ++prod_seg;
     const Segment* sg = P.segs + prod_seg;
-    const uint64_t p0 = (tile - sg->first_tile) * (uint64_t)kTilePts;
+    const uint64_t p0 = (tile - sg->first_tile) * (uint64_t)TP;
     const uint64_t rem = sg->n_points - p0;
-    const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
+    const uint32_t npts = rem < (uint64_t)TP ? (uint32_t)rem : (uint32_t)TP;
     const uint32_t bytes = (npts * (uint32_t)R + 15u) & ~15u;  // bulk copies move multiples of 16 bytes
     stage_tile[s] = tile;
     stage_seg[s] = prod_seg;
@@ -696,8 +701,28 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
       __syncthreads();
     }
     mbar_wait(&full_bar[s], parity);
-    SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
-    process_tile<MODE>(P, sseg, tile, src, acc, lch);
+    if constexpr (R == 12 && MODE == MODE_COUNT && TP == kTilePtsPos) {
+      const Segment& S = sseg;
+      const uint64_t rem = S.n_points - (tile - S.first_tile) * (uint64_t)TP;
+      const uint32_t npts = rem < (uint64_t)TP ? (uint32_t)rem : (uint32_t)TP;
+      const uint4* q = reinterpret_cast<const uint4*>(dsm + (size_t)s * kTileBytes + 48u * tid);  // records 4 tid .. 4 tid + 3
+      const uint4 a = q[0], b = q[1], c = q[2];
+      const uint32_t i0 = 4u * tid;
+      const int32_t x0 = (int32_t)a.x, y0 = (int32_t)a.y, z0 = (int32_t)a.z;
+      const int32_t x1 = (int32_t)a.w, y1 = (int32_t)b.x, z1 = (int32_t)b.y;
+      const int32_t x2 = (int32_t)b.z, y2 = (int32_t)b.w, z2 = (int32_t)c.x;
+      const int32_t x3 = (int32_t)c.y, y3 = (int32_t)c.z, z3 = (int32_t)c.w;
+      const int32_t lx = S.lo[0], hx = S.hi[0], ly = S.lo[1], hy = S.hi[1], lz = S.lo[2], hz = S.hi[2];
+      uint32_t n = 0;
+      n += (i0 + 0u < npts) & in_range(x0, lx, hx) & in_range(y0, ly, hy) & in_range(z0, lz, hz);
+      n += (i0 + 1u < npts) & in_range(x1, lx, hx) & in_range(y1, ly, hy) & in_range(z1, lz, hz);
+      n += (i0 + 2u < npts) & in_range(x2, lx, hx) & in_range(y2, ly, hy) & in_range(z2, lz, hz);
+      n += (i0 + 3u < npts) & in_range(x3, lx, hx) & in_range(y3, ly, hy) & in_range(z3, lz, hz);
+      acc += n;
+    } else {
+      SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
+      process_tile<MODE>(P, sseg, tile, src, acc, lch);
+    }
     __syncthreads();  // every thread is done reading stage s
     if (tid == 0) produce((int)s);
   }
@@ -1366,10 +1391,11 @@ static int persistent_grid(const void* kfn, size_t smem, int sm_count, uint64_t 
 
 template <int R, int MODE>
 static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
-  constexpr int STAGES = MODE == MODE_GRID ? 2 : ScanStages<R>::value;
-  constexpr size_t smem = (size_t)STAGES * kTilePts * R;
+  constexpr int TP = (R == 12 && MODE == MODE_COUNT) ? kTilePtsPos : kTilePts;
+  constexpr int STAGES = MODE == MODE_GRID ? 2 : (TP == kTilePtsPos ? 5 : ScanStages<R>::value);
+  constexpr size_t smem = (size_t)STAGES * TP * R;
   static bool configured = false;
-  auto kfn = k_scan_staged<R, MODE, STAGES>;
+  auto kfn = k_scan_staged<R, MODE, STAGES, TP>;
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
@@ -1427,8 +1453,10 @@ static int launch_select(const ScanParams& p, int align, int sm_count, cudaStrea
 bool staged_supports(uint32_t R) { return R == 12 || R == 20 || R == 26 || R == 28 || R == 34; }
 
 // records per scheduling unit ("tile") for a launch: 512 for count / grid, a look-back unit for select
-uint32_t tile_points(int /*variant*/, int mode, uint32_t /*R*/) {
-  return mode == MODE_SELECT ? (uint32_t)kSelUnitPts : (uint32_t)kTilePts;
+uint32_t tile_points(int variant, int mode, uint32_t R) {
+  if (mode == MODE_SELECT) return (uint32_t)kSelUnitPts;
+  if (mode == MODE_COUNT && variant == 2 && R == 12) return (uint32_t)kTilePtsPos;  // LAST positions, staged
+  return (uint32_t)kTilePts;
 }
 
 // variant: 1 = direct, 2 = staged (needs uniform_record_len supported); returns 0 ok, <0 CUDA error
