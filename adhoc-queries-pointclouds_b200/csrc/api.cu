@@ -653,7 +653,10 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
   const int mode = kind == PCQ_COLLECT_COUNT ? MODE_COUNT : (kind == PCQ_COLLECT_BUFFER ? MODE_SELECT : MODE_GRID);
 
   // number the scheduling units ("tiles") across the segments of the launch; lanes are contiguous runs
-  const uint32_t tile_pts = tile_points(variant, mode, R);
+  bool select_bytes = mode == MODE_SELECT && q->kind == PCQ_QUERY_CLASS && all_last;
+  for (const Segment& s : segs)
+    if ((reinterpret_cast<uintptr_t>(s.cls) & 15u) != 0) select_bytes = false;
+  const uint32_t tile_pts = tile_points(variant, mode, R, select_bytes);
   uint64_t n_tiles = 0;
   {
     std::vector<uint64_t> lane_first(n_collectors, ~0ull);
@@ -720,6 +723,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     P.cls = q->cls;
     P.n_tiles = n_tiles;
     P.tile_pts = tile_pts;
+    P.sel_bytes = select_bytes ? 1u : 0u;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
     if (mode == MODE_SELECT) {
       if (const char* e = std::getenv("PCQ_SELECT_DEBUG")) P.debug = (uint32_t)std::atoi(e);

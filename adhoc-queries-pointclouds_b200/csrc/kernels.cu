@@ -829,6 +829,13 @@ __device__ __forceinline__ uint32_t ldg_u8_h(const uint8_t* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint4 ldg_v4_h(const uint8_t* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void stg_v4_h(uint4* p, const uint4& v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
                "l"(pol)
@@ -926,10 +933,11 @@ __device__ __forceinline__ void select_compose(const Segment& S, const RawPoint&
   sts_point31(dst, wd);
 }
 
-// Emit the matches of consumer warp `w` in unit U (all 32 lanes call it).  `list` holds the unit-local
-// record index of the warp's r-th match.  Dense: lane l composes matches l and l + 32 of each round of 64.
-template <int AL>
-__device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_t* list, uint8_t* stage) {
+// Emit the matches of consumer warp `w` in unit U (all 32 lanes call it).  index_of(r) is the index, within the
+// warp's `warp_pts` consecutive records of the unit, of the warp's r-th match.  Dense: lane l composes matches l and
+// l + 32 of each round of 64.
+template <int AL, class IndexOf>
+__device__ __forceinline__ void select_emit_warp(const SelUnit& U, const IndexOf& index_of, uint32_t warp_pts, uint8_t* stage) {
   const uint32_t w = warp_id(), ln = lane_id();
   const uint32_t mine = U.warp_cnt[w];
   if (mine == 0) return;
@@ -937,14 +945,14 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
   for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
   const unsigned long long out0 = U.out_rec + before;
   const Segment& S = U.seg;
-  const uint64_t wbase = U.u0 + (uint64_t)w * kSelWarpPts;
+  const uint64_t wbase = U.u0 + (uint64_t)w * warp_pts;
   const uint64_t pol = l2_policy_drop();
   // the fields of round r + 1 are fetched (L2) while round r is composed and flushed
   RawPoint q0, q1;
   {
     const uint32_t n = min((uint32_t)kSelStageRecs, mine);
     // lanes beyond the round's records fetch the round's first record again (always a valid address)
-    select_fetch2<AL>(S, wbase + list[ln < n ? ln : 0u], wbase + list[ln + 32u < n ? ln + 32u : 0u], q0, q1, pol);
+    select_fetch2<AL>(S, wbase + index_of(ln < n ? ln : 0u), wbase + index_of(ln + 32u < n ? ln + 32u : 0u), q0, q1, pol);
   }
 #pragma unroll 1
   for (uint32_t base = 0; base < mine; base += kSelStageRecs) {
@@ -957,7 +965,7 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
     if (base + kSelStageRecs < mine) {
       const uint32_t nbase = base + kSelStageRecs;
       const uint32_t nn = min((uint32_t)kSelStageRecs, mine - nbase);
-      select_fetch2<AL>(S, wbase + list[nbase + (r0 < nn ? r0 : 0u)], wbase + list[nbase + (r1 < nn ? r1 : 0u)], q0, q1, pol);
+      select_fetch2<AL>(S, wbase + index_of(nbase + (r0 < nn ? r0 : 0u)), wbase + index_of(nbase + (r1 < nn ? r1 : 0u)), q0, q1, pol);
     }
     if (r0 < n) select_compose(S, p0, stage + phase + r0 * 31u);
     if (r1 < n) select_compose(S, p1, stage + phase + r1 * 31u);
@@ -980,17 +988,95 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const uint16_
   }
 }
 
-template <int AL>
-__global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
-  __shared__ SelUnit unit[kSelBufs];
-  __shared__ __align__(8) uint64_t bar_tk[kSelBufs];    // unit descriptor filled    (dispatcher -> consumers, look-back warp)
-  __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];   // all warp counts posted    (consumers -> look-back warp)
-  __shared__ __align__(8) uint64_t bar_pre[kSelBufs];   // exclusive prefix resolved (look-back warp -> consumers)
-  __shared__ __align__(8) uint64_t bar_free[kSelBufs];  // unit emitted              (consumers -> dispatcher)
-  __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
-  __shared__ uint16_t match_list[kSelWarps][kSelLag + 1][kSelWarpPts];  // unit-local index of each warp's r-th match
-
+// ---------------- dispatcher warp: tickets and unit descriptors, never blocked by a look-back ----------------
+template <int UNIT_PTS>
+__device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelUnit* unit, uint64_t* bar_tk, uint64_t* bar_free) {
   const uint32_t ln = lane_id();
+  uint32_t seg_cur = 0;
+  uint32_t end_marks = 0;  // every look-back warp needs to meet an end marker
+  for (uint32_t n = 0;; ++n) {
+    const uint32_t b = n % kSelBufs;
+    if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
+    unsigned long long tile = ~0ull;
+    if (end_marks == 0u) {
+      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+    SelUnit& U = unit[b];
+    if (ln == 0) U.acc = 0u;
+    if (tile >= P.n_tiles) {
+      if (ln == 0) {
+        U.tile = ~0ull;
+        mbar_arrive(&bar_tk[b]);
+      }
+      if (++end_marks == (uint32_t)kSelLbWarps) break;
+      continue;
+    }
+    while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
+    const Segment* sg = P.segs + seg_cur;
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
+    uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
+    for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+    if (ln == 0) {
+      const LaneDev* L = P.lanes + sg->lane;
+      const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)UNIT_PTS;
+      const uint64_t rem = sg->n_points - u0;
+      U.tile = tile;
+      U.u0 = u0;
+      U.npts = rem < (uint64_t)UNIT_PTS ? (uint32_t)rem : (uint32_t)UNIT_PTS;
+      U.out = L->out;
+      U.out_cap = L->out_cap;
+      U.out_base = L->out_base;
+      U.count = L->count;
+    }
+    __syncwarp();
+    if (ln == 0) mbar_arrive(&bar_tk[b]);
+  }
+}
+
+// ---------------- look-back warp(s): unit n is resolved by look-back warp n % kSelLbWarps ----------------
+__device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUnit* unit, uint64_t* bar_tk, uint64_t* bar_cnt,
+                                                     uint64_t* bar_pre) {
+  const uint32_t ln = lane_id();
+  for (uint32_t n = warp_id() - kSelWarps;; n += kSelLbWarps) {
+    const uint32_t b = n % kSelBufs;
+    const uint32_t par = (n / kSelBufs) & 1u;
+    mbar_wait(&bar_tk[b], par);
+    SelUnit& U = unit[b];
+    const unsigned long long tile = U.tile;
+    if (tile == ~0ull) break;
+    const uint64_t lane_first = U.seg.lane_first_tile;
+    mbar_wait(&bar_cnt[b], par);
+    uint32_t total = ln < (uint32_t)kSelWarps ? U.warp_cnt[ln] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    // (the unit's aggregate was published by the consumer warp that posted the last count)
+    unsigned long long excl = 0;
+    if (tile != lane_first && !(P.debug & 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
+    if (ln == 0) {
+      if (tile != lane_first) st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
+      U.out_rec = U.out_base + excl;
+      if (total) atomicAdd(U.count, (unsigned long long)total);
+      mbar_arrive(&bar_pre[b]);
+    }
+  }
+}
+
+// a consumer warp posts its match count of unit U; the warp that posts the last count publishes the unit's aggregate
+// right away, so that no look-back of another CTA ever waits behind one of this CTA's look-backs (lane 0 only)
+__device__ __forceinline__ void select_post_count(const ScanParams& P, SelUnit& U, uint32_t cnt, uint64_t* bar_cnt_b) {
+  U.warp_cnt[warp_id()] = cnt;
+  const uint32_t old = atomicAdd(&U.acc, cnt + (1u << 24));
+  if ((old >> 24) == (uint32_t)kSelWarps - 1u) {
+    const unsigned long long total = (unsigned long long)((old & 0xFFFFFFu) + cnt);
+    const unsigned long long st = U.tile == U.seg.lane_first_tile ? kStPrefix : kStAgg;  // first unit: prefix == aggregate
+    st_state(P.tile_state + U.tile, (st << kStatusShift) | total);
+  }
+  mbar_arrive(bar_cnt_b);
+}
+
+// the barriers of a select CTA
+__device__ __forceinline__ void select_init_barriers(uint64_t* bar_tk, uint64_t* bar_cnt, uint64_t* bar_pre, uint64_t* bar_free) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int b = 0; b < kSelBufs; ++b) {
@@ -1002,76 +1088,27 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
     mbar_fence_init();
   }
   __syncthreads();
+}
+
+template <int AL>
+__global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
+  __shared__ SelUnit unit[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_tk[kSelBufs];    // unit descriptor filled    (dispatcher -> consumers, look-back warp)
+  __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];   // all warp counts posted    (consumers -> look-back warp)
+  __shared__ __align__(8) uint64_t bar_pre[kSelBufs];   // exclusive prefix resolved (look-back warp -> consumers)
+  __shared__ __align__(8) uint64_t bar_free[kSelBufs];  // unit emitted              (consumers -> dispatcher)
+  __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
+  __shared__ uint16_t match_list[kSelWarps][kSelLag + 1][kSelWarpPts];  // unit-local index of each warp's r-th match
+
+  const uint32_t ln = lane_id();
+  select_init_barriers(bar_tk, bar_cnt, bar_pre, bar_free);
 
   if (warp_id() == kSelWarps + kSelLbWarps) {
-    // ---------------- dispatcher warp: tickets and unit descriptors, never blocked by a look-back ----------------
-    uint32_t seg_cur = 0;
-    uint32_t end_marks = 0;  // every look-back warp needs to meet an end marker
-    for (uint32_t n = 0;; ++n) {
-      const uint32_t b = n % kSelBufs;
-      if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
-      unsigned long long tile = ~0ull;
-      if (end_marks == 0u) {
-        if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-      }
-      SelUnit& U = unit[b];
-      if (ln == 0) U.acc = 0u;
-      if (tile >= P.n_tiles) {
-        if (ln == 0) {
-          U.tile = ~0ull;
-          mbar_arrive(&bar_tk[b]);
-        }
-        if (++end_marks == (uint32_t)kSelLbWarps) break;
-        continue;
-      }
-      while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
-      const Segment* sg = P.segs + seg_cur;
-      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
-      uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
-      for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
-      if (ln == 0) {
-        const LaneDev* L = P.lanes + sg->lane;
-        const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)kSelUnitPts;
-        const uint64_t rem = sg->n_points - u0;
-        U.tile = tile;
-        U.u0 = u0;
-        U.npts = rem < (uint64_t)kSelUnitPts ? (uint32_t)rem : (uint32_t)kSelUnitPts;
-        U.out = L->out;
-        U.out_cap = L->out_cap;
-        U.out_base = L->out_base;
-        U.count = L->count;
-      }
-      __syncwarp();
-      if (ln == 0) mbar_arrive(&bar_tk[b]);
-    }
+    select_dispatcher_warp<kSelUnitPts>(P, unit, bar_tk, bar_free);
     return;
   }
-
   if (warp_id() >= kSelWarps) {
-    // ---------------- look-back warps: one look-back takes a few L2 round trips, so two run interleaved ----------------
-    for (uint32_t n = warp_id() - kSelWarps;; n += kSelLbWarps) {
-      const uint32_t b = n % kSelBufs;
-      const uint32_t par = (n / kSelBufs) & 1u;
-      mbar_wait(&bar_tk[b], par);
-      SelUnit& U = unit[b];
-      const unsigned long long tile = U.tile;
-      if (tile == ~0ull) break;
-      const uint64_t lane_first = U.seg.lane_first_tile;
-      mbar_wait(&bar_cnt[b], par);
-      uint32_t total = ln < (uint32_t)kSelWarps ? U.warp_cnt[ln] : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      // (the unit's aggregate was published by the consumer warp that posted the last count)
-      unsigned long long excl = 0;
-      if (tile != lane_first && !(P.debug & 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
-      if (ln == 0) {
-        if (tile != lane_first) st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
-        U.out_rec = U.out_base + excl;
-        if (total) atomicAdd(U.count, (unsigned long long)total);
-        mbar_arrive(&bar_pre[b]);
-      }
-    }
+    select_lookback_warp(P, unit, bar_tk, bar_cnt, bar_pre);
     return;
   }
 
@@ -1136,18 +1173,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
         cnt += (uint32_t)__popc(bal);
       }
       __syncwarp();  // the list is read by other lanes when the unit is emitted
-      if (ln == 0) {
-        U.warp_cnt[w] = cnt;
-        // The warp that posts the last count publishes the unit's aggregate right away: no look-back of another
-        // CTA ever waits behind one of this CTA's look-backs.
-        const uint32_t old = atomicAdd(&U.acc, cnt + (1u << 24));
-        if ((old >> 24) == (uint32_t)kSelWarps - 1u) {
-          const unsigned long long total = (unsigned long long)((old & 0xFFFFFFu) + cnt);
-          const unsigned long long st = U.tile == S.lane_first_tile ? kStPrefix : kStAgg;  // first unit: prefix == aggregate
-          st_state(P.tile_state + U.tile, (st << kStatusShift) | total);
-        }
-        mbar_arrive(&bar_cnt[b]);
-      }
+      if (ln == 0) select_post_count(P, U, cnt, &bar_cnt[b]);
     }
     const uint32_t counted = cur ? n + 1u : n;  // units [0, counted) of this CTA are counted
     bool nxt = false;
@@ -1169,7 +1195,130 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
       } else if (!(P.debug & 4u) || !mbar_test(&bar_pre[pb], par)) {
         break;  // (debug 4: emit a younger unit early when its prefix is already there)
       }
-      if (!(P.debug & 2u)) select_emit_warp<AL>(unit[pb], match_list[w][emit_next % (uint32_t)(kSelLag + 1)], stage[w]);
+      if (!(P.debug & 2u)) {
+        const uint16_t* list = match_list[w][emit_next % (uint32_t)(kSelLag + 1)];
+        select_emit_warp<AL>(unit[pb], [list](uint32_t r) { return (uint32_t)list[r]; }, (uint32_t)kSelWarpPts, stage[w]);
+      }
+      __syncwarp();
+      if (ln == 0) mbar_arrive(&bar_free[pb]);
+      ++emit_next;
+    }
+    if (!nxt) break;
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MODE_SELECT for LAST class queries (last.rs:253-291): the predicate stream is ONE byte per point, so a 2048-point
+// unit would be 2 KB and the kernel would run at the unit rate of the look-back machinery, not at memory speed.
+// Same roles and barriers as k_select, but a unit is 32768 points: every consumer warp owns 4096 consecutive class
+// bytes as 8 rows of 32 lanes x 16 bytes (one 16-byte load per lane and row, SIMD byte compare).  Instead of an index
+// list the warp keeps, per lane and row, the 16-bit match mask and the number of matches before it; the emit finds
+// its r-th match with a binary search over those 256 prefixes and a find-nth-set-bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelBRows = 8;
+constexpr int kSelBWarpPts = kSelBRows * 32 * 16;       // 4096
+constexpr int kSelBUnitPts = kSelWarps * kSelBWarpPts;  // 32768
+constexpr int kSelBLag = 2;
+
+template <int AL>
+__global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
+  __shared__ SelUnit unit[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_tk[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_pre[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_free[kSelBufs];
+  __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
+  __shared__ uint16_t m_mask[kSelWarps][kSelBLag + 1][kSelBRows * 32];  // match mask of (row, lane)
+  __shared__ uint16_t m_pre[kSelWarps][kSelBLag + 1][kSelBRows * 32];   // matches of the warp before (row, lane)
+
+  const uint32_t ln = lane_id();
+  select_init_barriers(bar_tk, bar_cnt, bar_pre, bar_free);
+  if (warp_id() == kSelWarps + kSelLbWarps) {
+    select_dispatcher_warp<kSelBUnitPts>(P, unit, bar_tk, bar_free);
+    return;
+  }
+  if (warp_id() >= kSelWarps) {
+    select_lookback_warp(P, unit, bar_tk, bar_cnt, bar_pre);
+    return;
+  }
+
+  const uint32_t w = warp_id();
+  const uint32_t pat = (P.cls & 0xFFu) * 0x01010101u;
+  const uint64_t pol_keep = l2_policy_keep();
+  uint4 v[kSelBRows];
+  uint32_t npts = 0;
+  auto issue_loads = [&](const SelUnit& U) {
+    npts = U.npts;
+    const uint8_t* col = U.seg.cls + U.u0 + (uint64_t)w * kSelBWarpPts;
+#pragma unroll
+    for (int k = 0; k < kSelBRows; ++k) {
+      const uint32_t i = (uint32_t)k * 512u + ln * 16u;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      // a partly valid 16-byte group is still loadable: columns are followed by other columns or by padding
+      if (w * kSelBWarpPts + i < npts) v[k] = ldg_v4_h(col + i, pol_keep);
+    }
+  };
+  auto nibble = [&](uint32_t wd) -> uint32_t { return ((__vcmpeq4(wd, pat) & 0x08040201u) * 0x01010101u) >> 24; };
+
+  mbar_wait(&bar_tk[0], 0u);
+  bool cur = unit[0].tile != ~0ull;
+  if (cur) issue_loads(unit[0]);
+  uint32_t emit_next = 0;
+  for (uint32_t n = 0;; ++n) {
+    const uint32_t b = n % kSelBufs;
+    if (cur) {
+      SelUnit& U = unit[b];
+      uint16_t* mk = m_mask[w][n % (uint32_t)(kSelBLag + 1)];
+      uint16_t* pr = m_pre[w][n % (uint32_t)(kSelBLag + 1)];
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kSelBRows; ++k) {
+        const uint32_t gi = w * kSelBWarpPts + (uint32_t)k * 512u + ln * 16u;
+        uint32_t m16 = nibble(v[k].x) | (nibble(v[k].y) << 4) | (nibble(v[k].z) << 8) | (nibble(v[k].w) << 12);
+        const uint32_t valid = gi < npts ? min(16u, npts - gi) : 0u;
+        m16 &= (1u << valid) - 1u;
+        const uint32_t c = (uint32_t)__popc(m16);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (ln >= (uint32_t)o) incl += t;
+        }
+        mk[k * 32 + ln] = (uint16_t)m16;
+        pr[k * 32 + ln] = (uint16_t)(cnt + incl - c);
+        cnt += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      __syncwarp();
+      if (ln == 0) select_post_count(P, U, cnt, &bar_cnt[b]);
+    }
+    const uint32_t counted = cur ? n + 1u : n;
+    bool nxt = false;
+    if (cur) {
+      const uint32_t nb = (n + 1u) % kSelBufs;
+      mbar_wait(&bar_tk[nb], ((n + 1u) / kSelBufs) & 1u);
+      nxt = unit[nb].tile != ~0ull;
+      if (nxt) issue_loads(unit[nb]);
+    }
+    while (emit_next < counted) {
+      const uint32_t pb = emit_next % kSelBufs;
+      const uint32_t par = (emit_next / kSelBufs) & 1u;
+      if (nxt && emit_next + (uint32_t)kSelBLag >= counted) break;
+      mbar_wait(&bar_pre[pb], par);
+      if (!(P.debug & 2u)) {
+        const uint16_t* mk = m_mask[w][emit_next % (uint32_t)(kSelBLag + 1)];
+        const uint16_t* pr = m_pre[w][emit_next % (uint32_t)(kSelBLag + 1)];
+        auto index_of = [mk, pr](uint32_t r) -> uint32_t {
+          uint32_t lo = 0, hi = (uint32_t)kSelBRows * 32u;  // first entry whose prefix exceeds r
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)pr[mid] > r) hi = mid; else lo = mid + 1u;
+          }
+          const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
+          return e * 16u + __fns((uint32_t)mk[e], 0u, (int)(r - (uint32_t)pr[e]) + 1);
+        };
+        select_emit_warp<AL>(unit[pb], index_of, (uint32_t)kSelBWarpPts, stage[w]);
+      }
       __syncwarp();
       if (ln == 0) mbar_arrive(&bar_free[pb]);
       ++emit_next;
@@ -1443,8 +1592,25 @@ static int launch_select_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   kfn<<<grid, kSelThreads, 0, st>>>(p);
   return check_launch();
 }
+template <int AL>
+static int launch_select_bytes_t(const ScanParams& p, int sm_count, cudaStream_t st) {
+  auto kfn = k_select_bytes<AL>;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kSelThreads, 0) != cudaSuccess) return -1;
+  if (per_sm < 1) per_sm = 1;
+  uint64_t g = (uint64_t)sm_count * (uint64_t)per_sm;
+  if (g > p.n_tiles) g = p.n_tiles;
+  if (g == 0) return 0;
+  kfn<<<(unsigned)g, kSelThreads, 0, st>>>(p);
+  return check_launch();
+}
 // `align` = alignment every x/y/z field of every segment of the launch is guaranteed to have (4, 2 or 1)
 static int launch_select(const ScanParams& p, int align, int sm_count, cudaStream_t st) {
+  if (p.sel_bytes) {
+    if (align >= 4) return launch_select_bytes_t<4>(p, sm_count, st);
+    if (align >= 2) return launch_select_bytes_t<2>(p, sm_count, st);
+    return launch_select_bytes_t<1>(p, sm_count, st);
+  }
   if (align >= 4) return launch_select_t<4>(p, sm_count, st);
   if (align >= 2) return launch_select_t<2>(p, sm_count, st);
   return launch_select_t<1>(p, sm_count, st);
@@ -1453,8 +1619,8 @@ static int launch_select(const ScanParams& p, int align, int sm_count, cudaStrea
 bool staged_supports(uint32_t R) { return R == 12 || R == 20 || R == 26 || R == 28 || R == 34; }
 
 // records per scheduling unit ("tile") for a launch: 512 for count / grid, a look-back unit for select
-uint32_t tile_points(int variant, int mode, uint32_t R) {
-  if (mode == MODE_SELECT) return (uint32_t)kSelUnitPts;
+uint32_t tile_points(int variant, int mode, uint32_t R, bool select_bytes) {
+  if (mode == MODE_SELECT) return select_bytes ? (uint32_t)kSelBUnitPts : (uint32_t)kSelUnitPts;
   if (mode == MODE_COUNT && variant == 2 && R == 12) return (uint32_t)kTilePtsPos;  // LAST positions, staged
   return (uint32_t)kTilePts;
 }

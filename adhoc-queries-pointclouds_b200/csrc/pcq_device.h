@@ -117,12 +117,14 @@ struct ScanParams {
   const LaneDev* lanes;
   unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
   unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
+  uint32_t sel_bytes;              // MODE_SELECT: 1 = k_select_bytes (LAST class query, 32768-point units)
   uint32_t debug;                  // measurement only (PCQ_SELECT_DEBUG): 1 = skip the look-back, 2 = skip the emit
 };
 
 // launch wrappers implemented in kernels.cu (stream is a cudaStream_t); 0 = ok, < 0 = CUDA error
 bool staged_supports(uint32_t record_len);
-uint32_t tile_points(int variant, int mode, uint32_t record_len);
+// select_bytes: MODE_SELECT launch of a class query over LAST segments whose class columns are 16-byte aligned
+uint32_t tile_points(int variant, int mode, uint32_t record_len, bool select_bytes);
 int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_record_len, int min_align, int sm_count,
                 void* stream);
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
