@@ -306,13 +306,17 @@ def main():
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
         try:
-            traffic = json.loads(tr.read_text()).get("scan_count_dram_bytes_per_launch")
+            # DRAM bytes per launch = this launch size x the dram/algorithmic ratio of the committed `ncu --set full`
+            # capture of the same kernel (profiles/traffic.json; captured on a 16 x 8 M-point dataset)
+            ratio = json.loads(tr.read_text()).get("scan_count_dram_to_algorithmic_ratio")
+            traffic = None if ratio is None else float(ratio) * bytes_per_launch
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_scan_staged<28,COUNT> (k_scan_direct when --variant 1)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kernel_ms,
-                "note": "average over the S, L and XL launches of the timed region (5 / 30 / 64 tiles of 875 MB)"}
+                "note": "average over the S, L and XL launches of the timed region (5 / 30 / 64 tiles of 875 MB); traffic = "
+                        "algorithmic bytes x the dram/algorithmic ratio of the committed ncu capture (profiles/traffic.json)"}
 
     # ---- e2e: pinned host file images -> H2D -> scan -> counts to the host, every step ----
     e2e = None
