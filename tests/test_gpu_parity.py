@@ -124,6 +124,51 @@ def test_ragged_sizes(pcq, ctx, n):
             assert_same(kind, got, want)
 
 
+@pytest.mark.parametrize("layout", ["las", "last"])
+def test_select_many_small_files(pcq, ctx, layout):
+    """look-back units never straddle files: 150 files of ragged sizes (empty ones included), one collector over all
+    of them and one collector per file, bounds and class queries (LAST class queries take k_select_bytes)"""
+    rng = np.random.default_rng(2024 + (layout == "last"))
+    sizes = [int(v) for v in rng.integers(0, 6000, size=146)] + [0, 1, 40_000, 70_001]
+    files = [random_file(rng, n, 1 + 2 * (k % 2), layout, 1) for k, n in enumerate(sizes)]
+    exts = [layout] * len(files)
+    b = box(1, 20_000, 120_000)
+    for kind in (orc.COLLECT_COUNT, orc.COLLECT_BUFFER):
+        for per_file in (False, True):
+            want = oracle_run(files, exts, kind, bounds=b, per_file=per_file)
+            got = gpu_run(pcq, ctx, files, exts, kind, bounds=b, per_file=per_file)
+            assert_same(kind, got, want)
+            for klass in (2, 19):
+                want = oracle_run(files, exts, kind, cls=klass, per_file=per_file)
+                got = gpu_run(pcq, ctx, files, exts, kind, cls=klass, per_file=per_file)
+                assert_same(kind, got, want)
+
+
+def test_last_class_select_multi_unit(pcq, ctx):
+    """k_select_bytes: several 32768-point units per CTA, a ragged tail, host-streamed chunks and a class column
+    whose address is not 16-byte aligned (falls back to k_select)"""
+    import torch
+
+    rng = np.random.default_rng(77)
+    n = 3_000_017
+    f = random_file(rng, n, 3, "last", 2)
+    for klass in (2, 6, 19):
+        want = oracle_run([f], ["last"], orc.COLLECT_BUFFER, cls=klass)
+        got = gpu_run(pcq, ctx, [f], ["last"], orc.COLLECT_BUFFER, cls=klass)
+        assert_same(orc.COLLECT_BUFFER, got, want)
+    want = oracle_run([f], ["last"], orc.COLLECT_BUFFER, cls=6)
+    got = gpu_run(pcq, ctx, [f], ["last"], orc.COLLECT_BUFFER, cls=6, host_stream=True)
+    assert_same(orc.COLLECT_BUFFER, got, want)
+    # the whole transposed block wrapped in place: the class column starts at base + 15 N (odd)
+    desc = pcq.FileDesc()
+    pcq.binding.check(pcq.lib.pcq_parse_header(C.c_void_p(f.ctypes.data), f.nbytes, 1, 1, C.byref(desc)))
+    body = torch.from_numpy(f[desc.point_data_off:].copy()).to(f"cuda:{ctx.device}")
+    df = pcq.DeviceFile.wrap(ctx, desc, body.data_ptr(), keepalive=body)
+    c = pcq.BufferCollector(ctx)
+    pcq.ClassSearcher(6).search_files([df], _impl(pcq), [c])
+    assert same_point_seq(c.points(), want[0].points())
+
+
 def test_odd_record_lengths_and_extended_formats(pcq, ctx):
     rng = np.random.default_rng(5)
     for fmt, rl, ver in ((0, 23, (1, 2)), (1, 31, (1, 2)), (2, 29, (1, 2)), (3, 40, (1, 3)), (6, 30, (1, 4)), (7, 36, (1, 4))):
