@@ -267,7 +267,7 @@ void fill_segment(Segment* s, const pcq_file_desc& d, const uint8_t* rec, const 
 }
 
 int ensure_tile_state(pcq_ctx* ctx, uint64_t n_tiles) {
-  const uint64_t need = n_tiles + 2;
+  const uint64_t need = n_tiles * kDescStride + 2 * kDescStride;
   if (ctx->tile_state_cap < need) {
     if (ctx->tile_state) cudaFree(ctx->tile_state);
     ctx->tile_state = nullptr;
@@ -724,12 +724,14 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     P.n_tiles = n_tiles;
     P.tile_pts = tile_pts;
     P.sel_bytes = select_bytes ? 1u : 0u;
+    // uniform record length + 16-byte aligned ranges (staged_ok) and a predicate that lives in the staged records
+    P.sel_ring = (mode == MODE_SELECT && variant == 2 && !select_bytes) ? R : 0u;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
     if (mode == MODE_SELECT) {
       if (const char* e = std::getenv("PCQ_SELECT_DEBUG")) P.debug = (uint32_t)std::atoi(e);
       RC(ensure_tile_state(ctx, n_tiles));
       P.ticket = ctx->tile_state;
-      P.tile_state = ctx->tile_state + 1;
+      P.tile_state = ctx->tile_state + kDescStride;
     }
 
     int lrc;

@@ -222,6 +222,21 @@ __device__ __forceinline__ void point_words(const Segment& S, const Hit& h, cons
   w[7] = (rgb[2] & 0xFFFFu) | ((h.cls & 0xFFu) << 16);
 }
 
+// position of the n-th (0-based) set bit of `mask` (which has more than n bits set): five popc steps
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t n) {
+  uint32_t pos = 0;
+  uint32_t c = (uint32_t)__popc(mask & 0xFFFFu);
+  if (n >= c) { n -= c; pos += 16u; mask >>= 16; }
+  c = (uint32_t)__popc(mask & 0xFFu);
+  if (n >= c) { n -= c; pos += 8u; mask >>= 8; }
+  c = (uint32_t)__popc(mask & 0xFu);
+  if (n >= c) { n -= c; pos += 4u; mask >>= 4; }
+  c = (uint32_t)__popc(mask & 0x3u);
+  if (n >= c) { n -= c; pos += 2u; mask >>= 2; }
+  if (n >= (mask & 1u)) pos += 1u;
+  return pos;
+}
+
 // Store a 31-byte record at an arbitrarily aligned shared-memory address as 7 word stores, one 16-bit
 // store and one byte store (w[j] = record bytes 4j .. 4j+3, top byte of w[7] zero).
 __device__ __forceinline__ void sts_point31(uint8_t* dst, const uint32_t w[8]) {
@@ -294,7 +309,7 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
 #pragma unroll
       for (int k = 0; k < kLookback; ++k) {
         const long long t = hi - (long long)(32u * (uint32_t)k + ln);
-        sv[k] = t >= lo ? ld_state(state + t) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
+        sv[k] = t >= lo ? ld_state(state + t * (long long)kDescStride) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
         pending |= (sv[k] >> kStatusShift) == 0ull;
       }
     } while (__any_sync(0xffffffffu, pending));
@@ -781,7 +796,7 @@ struct SelUnit {
   unsigned long long* count;
   uint32_t npts;
   uint32_t acc;  // consumers: sum of posted warp counts | number of posted warps << 24
-  uint32_t warp_cnt[kSelWarps];
+  uint32_t warp_cnt[16];  // one per consumer warp (8 in k_select / k_select_bytes, 16 in k_select_ring)
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -1035,10 +1050,11 @@ __device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelU
 }
 
 // ---------------- look-back warp(s): unit n is resolved by look-back warp n % kSelLbWarps ----------------
+template <int NW = kSelWarps>
 __device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUnit* unit, uint64_t* bar_tk, uint64_t* bar_cnt,
                                                      uint64_t* bar_pre) {
   const uint32_t ln = lane_id();
-  for (uint32_t n = warp_id() - kSelWarps;; n += kSelLbWarps) {
+  for (uint32_t n = warp_id() - NW;; n += kSelLbWarps) {
     const uint32_t b = n % kSelBufs;
     const uint32_t par = (n / kSelBufs) & 1u;
     mbar_wait(&bar_tk[b], par);
@@ -1047,14 +1063,14 @@ __device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUni
     if (tile == ~0ull) break;
     const uint64_t lane_first = U.seg.lane_first_tile;
     mbar_wait(&bar_cnt[b], par);
-    uint32_t total = ln < (uint32_t)kSelWarps ? U.warp_cnt[ln] : 0u;
+    uint32_t total = ln < (uint32_t)NW ? U.warp_cnt[ln] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     // (the unit's aggregate was published by the consumer warp that posted the last count)
     unsigned long long excl = 0;
     if (tile != lane_first && !(P.debug & 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
     if (ln == 0) {
-      if (tile != lane_first) st_state(P.tile_state + tile, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
+      if (tile != lane_first) st_state(P.tile_state + tile * kDescStride, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
       U.out_rec = U.out_base + excl;
       if (total) atomicAdd(U.count, (unsigned long long)total);
       mbar_arrive(&bar_pre[b]);
@@ -1064,26 +1080,28 @@ __device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUni
 
 // a consumer warp posts its match count of unit U; the warp that posts the last count publishes the unit's aggregate
 // right away, so that no look-back of another CTA ever waits behind one of this CTA's look-backs (lane 0 only)
+template <int NW = kSelWarps>
 __device__ __forceinline__ void select_post_count(const ScanParams& P, SelUnit& U, uint32_t cnt, uint64_t* bar_cnt_b) {
   U.warp_cnt[warp_id()] = cnt;
   const uint32_t old = atomicAdd(&U.acc, cnt + (1u << 24));
-  if ((old >> 24) == (uint32_t)kSelWarps - 1u) {
+  if ((old >> 24) == (uint32_t)NW - 1u) {
     const unsigned long long total = (unsigned long long)((old & 0xFFFFFFu) + cnt);
     const unsigned long long st = U.tile == U.seg.lane_first_tile ? kStPrefix : kStAgg;  // first unit: prefix == aggregate
-    st_state(P.tile_state + U.tile, (st << kStatusShift) | total);
+    st_state(P.tile_state + U.tile * kDescStride, (st << kStatusShift) | total);
   }
   mbar_arrive(bar_cnt_b);
 }
 
 // the barriers of a select CTA
+template <int NW = kSelWarps>
 __device__ __forceinline__ void select_init_barriers(uint64_t* bar_tk, uint64_t* bar_cnt, uint64_t* bar_pre, uint64_t* bar_free) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int b = 0; b < kSelBufs; ++b) {
       mbar_init(&bar_tk[b], 1u);
-      mbar_init(&bar_cnt[b], (uint32_t)kSelWarps);
+      mbar_init(&bar_cnt[b], (uint32_t)NW);
       mbar_init(&bar_pre[b], 1u);
-      mbar_init(&bar_free[b], (uint32_t)kSelWarps);
+      mbar_init(&bar_free[b], (uint32_t)NW);
     }
     mbar_fence_init();
   }
@@ -1209,6 +1227,180 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_select_ring<R>: k_select for launches whose segments all have record length R and 16-byte aligned ranges
+// (LAS records, or LAST positions with R = 12, bounds queries and LAS class queries).
+// In k_select the predicate fields of the next unit wait in REGISTERS (24 per thread), which bounds the bytes in
+// flight per SM at ~114 KB — enough for a pure scan, not enough once consumers also wait for look-backs and emit.
+// Here the dispatcher streams every unit global -> shared with one bulk async copy (cp.async.bulk + mbarrier
+// complete_tx, the scan kernels' mechanism) into a ring of unit-sized slots, so 140-170 KB stay in flight whatever
+// the consumers are doing; 16 consumer warps read the predicate from shared memory without bank conflicts and
+// release the slot right after the ballots.  Units are 80-93 KB of records whatever the record length (the
+// look-back machinery resolves a fixed number of units per microsecond GPU-wide, so bytes per unit are what turns
+// that rate into bandwidth).  Emit, look-back and barriers are k_select's.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelRWarps = 16;
+constexpr int kSelRThreads = (kSelRWarps + kSelLbWarps + 1) * 32;
+constexpr int kSelRSlots = 2;  // unit-sized ring slots (the next unit lands while the current one is balloted)
+
+template <int R>
+struct SelRing {
+  static constexpr int rows = (int)sel_ring_rows(R);           // rows of 32 records per consumer warp and unit
+  static constexpr int warp_pts = 32 * rows;
+  static constexpr int unit_pts = kSelRWarps * warp_pts;       // == sel_ring_unit_points(R): 80-93 KB of records
+  static constexpr uint32_t slot_bytes = (uint32_t)unit_pts * (uint32_t)R;
+  static constexpr size_t smem = (size_t)kSelRSlots * slot_bytes + (size_t)kSelRWarps * kSelStageBytes;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
+  constexpr int AL = (R % 4 == 0) ? 4 : 2;  // a 16-byte aligned range of R-byte records
+  constexpr int RS = kSelRSlots;
+  constexpr int ROWS = SelRing<R>::rows;
+  constexpr int WPTS = SelRing<R>::warp_pts;
+  constexpr int UNIT = SelRing<R>::unit_pts;
+  constexpr uint32_t kSlotBytes = SelRing<R>::slot_bytes;
+  __shared__ SelUnit unit[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_tk[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_pre[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_free[kSelBufs];
+  __shared__ __align__(8) uint64_t bar_full[RS];   // the unit's records have landed   (bulk copy -> consumers)
+  __shared__ __align__(8) uint64_t bar_sfree[RS];  // the slot has been balloted        (consumers -> dispatcher)
+  // ballot mask of every (warp, row) of the units that are counted but not emitted yet: 60 bytes per warp and unit
+  // replace an index list; the emit finds its r-th match with a scan over the row counts and a find-nth-set-bit
+  __shared__ uint32_t m_bal[kSelRWarps][kSelLag + 1][ROWS];
+  __shared__ uint16_t m_run[kSelRWarps][kSelLag + 1][ROWS];  // matches of the warp before row k
+  extern __shared__ __align__(128) uint8_t sel_ring_dsm[];
+  uint8_t* ring = sel_ring_dsm;
+  uint8_t(*stage)[kSelStageBytes] = reinterpret_cast<uint8_t(*)[kSelStageBytes]>(sel_ring_dsm + (size_t)RS * kSlotBytes);
+
+  const uint32_t ln = lane_id();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < RS; ++s) {
+      mbar_init(&bar_full[s], 1u);
+      mbar_init(&bar_sfree[s], (uint32_t)kSelRWarps);
+    }
+  }
+  select_init_barriers<kSelRWarps>(bar_tk, bar_cnt, bar_pre, bar_free);  // (fences and synchronises the CTA)
+
+  if (warp_id() == kSelRWarps + kSelLbWarps) {
+    // ---------------- dispatcher warp: tickets, unit descriptors and the bulk copies ----------------
+    uint32_t seg_cur = 0;
+    for (uint32_t n = 0;; ++n) {
+      const uint32_t b = n % kSelBufs;
+      if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
+      unsigned long long tile = 0;
+      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      SelUnit& U = unit[b];
+      if (ln == 0) U.acc = 0u;
+      if (tile >= P.n_tiles) {
+        if (ln == 0) {
+          U.tile = ~0ull;
+          mbar_arrive(&bar_tk[b]);
+        }
+        break;
+      }
+      while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
+      const Segment* sg = P.segs + seg_cur;
+      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
+      for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+      const uint32_t slot = n % (uint32_t)RS;
+      if (n >= (uint32_t)RS) mbar_wait(&bar_sfree[slot], (n / (uint32_t)RS - 1u) & 1u);
+      if (ln == 0) {
+        const LaneDev* L = P.lanes + sg->lane;
+        const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)UNIT;
+        const uint64_t rem = sg->n_points - u0;
+        const uint32_t npts = rem < (uint64_t)UNIT ? (uint32_t)rem : (uint32_t)UNIT;
+        U.tile = tile;
+        U.u0 = u0;
+        U.npts = npts;
+        U.out = L->out;
+        U.out_cap = L->out_cap;
+        U.out_base = L->out_base;
+        U.count = L->count;
+        const uint32_t bytes = (npts * (uint32_t)R + 15u) & ~15u;  // bulk copies move multiples of 16 bytes
+        mbar_arrive_expect_tx(&bar_full[slot], bytes);
+        bulk_copy_g2s(ring + (size_t)slot * kSlotBytes, sg->rec + u0 * (uint64_t)R, bytes, &bar_full[slot]);
+      }
+      __syncwarp();
+      if (ln == 0) mbar_arrive(&bar_tk[b]);
+    }
+    return;
+  }
+  if (warp_id() >= kSelRWarps) {
+    select_lookback_warp<kSelRWarps>(P, unit, bar_tk, bar_cnt, bar_pre);
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const uint32_t w = warp_id();
+  uint32_t emit_next = 0, counted = 0;
+  auto emit_one = [&]() {
+    const uint32_t pb = emit_next % kSelBufs;
+    mbar_wait(&bar_pre[pb], (emit_next / kSelBufs) & 1u);
+    if (!(P.debug & 2u)) {
+      const uint32_t* bal = m_bal[w][emit_next % (uint32_t)(kSelLag + 1)];
+      const uint16_t* run = m_run[w][emit_next % (uint32_t)(kSelLag + 1)];
+      auto index_of = [bal, run](uint32_t r) -> uint32_t {
+        uint32_t k = 0;  // last row whose first match is not beyond r
+#pragma unroll
+        for (int j = 1; j < ROWS; ++j) k += (uint32_t)run[j] <= r ? 1u : 0u;  // run[] is non-decreasing
+        return k * 32u + nth_set_bit(bal[k], r - (uint32_t)run[k]);
+      };
+      select_emit_warp<AL>(unit[pb], index_of, (uint32_t)WPTS, stage[w]);
+    }
+    __syncwarp();
+    if (ln == 0) mbar_arrive(&bar_free[pb]);
+    ++emit_next;
+  };
+  for (uint32_t n = 0;; ++n) {
+    const uint32_t b = n % kSelBufs;
+    mbar_wait(&bar_tk[b], (n / kSelBufs) & 1u);
+    SelUnit& U = unit[b];
+    if (U.tile == ~0ull) break;
+    const uint32_t slot = n % (uint32_t)RS;
+    mbar_wait(&bar_full[slot], (n / (uint32_t)RS) & 1u);
+    {
+      const Segment& S = U.seg;
+      const uint32_t npts = U.npts;
+      const uint8_t* rec = ring + (size_t)slot * kSlotBytes + (size_t)(w * WPTS) * R;
+      uint32_t* bal_out = m_bal[w][n % (uint32_t)(kSelLag + 1)];
+      uint16_t* run_out = m_run[w][n % (uint32_t)(kSelLag + 1)];
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        const uint32_t il = (uint32_t)k * 32u + ln;  // index within the warp's records
+        const uint8_t* p = rec + il * R;
+        bool m = w * WPTS + il < npts;  // (beyond the unit's end the slot holds stale bytes)
+        if (P.query_kind == PCQ_QUERY_BOUNDS) {
+          const int32_t x = SmemSrc<R>::lds_i32(p), y = SmemSrc<R>::lds_i32(p + 4), z = SmemSrc<R>::lds_i32(p + 8);
+          m = m & in_range(x, S.lo[0], S.hi[0]) & in_range(y, S.lo[1], S.hi[1]) & in_range(z, S.lo[2], S.hi[2]);
+        } else {
+          m = m & ((uint32_t)p[S.cls_off] == P.cls);  // LAS records only (LAST class queries never come here)
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (ln == 0) {
+          bal_out[k] = bal;
+          run_out[k] = (uint16_t)cnt;
+        }
+        cnt += (uint32_t)__popc(bal);
+      }
+      __syncwarp();  // the masks are read by every lane when the unit is emitted; the slot is no longer needed
+      if (ln == 0) {
+        mbar_arrive(&bar_sfree[slot]);
+        select_post_count<kSelRWarps>(P, U, cnt, &bar_cnt[b]);
+      }
+    }
+    counted = n + 1u;
+    while (emit_next + (uint32_t)kSelLag < counted) emit_one();
+  }
+  while (emit_next < counted) emit_one();
+}
+
+// ------------------------------------------------------------------------------------------------
 // MODE_SELECT for LAST class queries (last.rs:253-291): the predicate stream is ONE byte per point, so a 2048-point
 // unit would be 2 KB and the kernel would run at the unit rate of the look-back machinery, not at memory speed.
 // Same roles and barriers as k_select, but a unit is 32768 points: every consumer warp owns 4096 consecutive class
@@ -1315,7 +1507,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
             if ((uint32_t)pr[mid] > r) hi = mid; else lo = mid + 1u;
           }
           const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
-          return e * 16u + __fns((uint32_t)mk[e], 0u, (int)(r - (uint32_t)pr[e]) + 1);
+          return e * 16u + nth_set_bit((uint32_t)mk[e], r - (uint32_t)pr[e]);
         };
         select_emit_warp<AL>(unit[pb], index_of, (uint32_t)kSelBWarpPts, stage[w]);
       }
@@ -1604,8 +1796,31 @@ static int launch_select_bytes_t(const ScanParams& p, int sm_count, cudaStream_t
   kfn<<<(unsigned)g, kSelThreads, 0, st>>>(p);
   return check_launch();
 }
+template <int R>
+static int launch_select_ring_t(const ScanParams& p, int sm_count, cudaStream_t st) {
+  auto kfn = k_select_ring<R>;
+  constexpr size_t smem = SelRing<R>::smem;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  uint64_t g = (uint64_t)sm_count;  // one CTA per SM, all resident
+  if (g > p.n_tiles) g = p.n_tiles;
+  if (g == 0) return 0;
+  kfn<<<(unsigned)g, kSelRThreads, smem, st>>>(p);
+  return check_launch();
+}
 // `align` = alignment every x/y/z field of every segment of the launch is guaranteed to have (4, 2 or 1)
 static int launch_select(const ScanParams& p, int align, int sm_count, cudaStream_t st) {
+  switch (p.sel_ring) {  // record length of a launch that qualifies for k_select_ring, else 0
+    case 12: return launch_select_ring_t<12>(p, sm_count, st);
+    case 20: return launch_select_ring_t<20>(p, sm_count, st);
+    case 26: return launch_select_ring_t<26>(p, sm_count, st);
+    case 28: return launch_select_ring_t<28>(p, sm_count, st);
+    case 34: return launch_select_ring_t<34>(p, sm_count, st);
+    default: break;
+  }
   if (p.sel_bytes) {
     if (align >= 4) return launch_select_bytes_t<4>(p, sm_count, st);
     if (align >= 2) return launch_select_bytes_t<2>(p, sm_count, st);
@@ -1620,7 +1835,11 @@ bool staged_supports(uint32_t R) { return R == 12 || R == 20 || R == 26 || R == 
 
 // records per scheduling unit ("tile") for a launch: 512 for count / grid, a look-back unit for select
 uint32_t tile_points(int variant, int mode, uint32_t R, bool select_bytes) {
-  if (mode == MODE_SELECT) return select_bytes ? (uint32_t)kSelBUnitPts : (uint32_t)kSelUnitPts;
+  if (mode == MODE_SELECT) {
+    if (select_bytes) return (uint32_t)kSelBUnitPts;
+    if (variant == 2 && staged_supports(R)) return sel_ring_unit_points(R);  // k_select_ring
+    return (uint32_t)kSelUnitPts;
+  }
   if (mode == MODE_COUNT && variant == 2 && R == 12) return (uint32_t)kTilePtsPos;  // LAST positions, staged
   return (uint32_t)kTilePts;
 }

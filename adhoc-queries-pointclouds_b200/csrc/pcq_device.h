@@ -87,6 +87,18 @@ struct GridDev {
 constexpr uint32_t kCandChunk = 64;
 constexpr uint32_t kGridCtasPerSm = 4;  // upper bound of resident scan CTAs per SM in grid mode
 
+// k_select_ring: rows of 32 records per consumer warp (16 of them) and unit, chosen so that a unit is 80-93 KB
+// (an even number of rows: the emit works in rounds of 64 records)
+constexpr uint32_t sel_ring_rows(uint32_t R) { return R <= 12 ? 14u : (R <= 20 ? 8u : (R <= 28 ? 6u : 4u)); }
+constexpr uint32_t sel_ring_unit_points(uint32_t R) { return 16u * 32u * sel_ring_rows(R); }
+
+// Look-back descriptors are spread out: one descriptor every kDescStride 8-byte words, so that the few hundred
+// descriptors every look-back warp of the GPU is polling at any moment do not all live in a handful of L2 lines.
+#ifndef PCQ_DESC_STRIDE
+#define PCQ_DESC_STRIDE 4
+#endif
+constexpr uint32_t kDescStride = PCQ_DESC_STRIDE;
+
 constexpr uint32_t kFlagCandOverflow = 2u;
 constexpr uint32_t kFlagHashFull = 4u;
 constexpr uint32_t kFlagLogOverflow = 8u;
@@ -118,6 +130,7 @@ struct ScanParams {
   unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
   unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
   uint32_t sel_bytes;              // MODE_SELECT: 1 = k_select_bytes (LAST class query, 32768-point units)
+  uint32_t sel_ring;               // MODE_SELECT: record length when the launch qualifies for k_select_ring, else 0
   uint32_t debug;                  // measurement only (PCQ_SELECT_DEBUG): 1 = skip the look-back, 2 = skip the emit
 };
 
