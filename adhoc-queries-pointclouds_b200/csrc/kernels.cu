@@ -398,6 +398,27 @@ __device__ __forceinline__ unsigned long long cand_reserve(const GridDev& g, Can
   return r;
 }
 
+// rare path, kept out of line so that it costs the insert kernel neither registers nor instruction-cache space
+template <class Src>
+__device__ __noinline__ void grid_log_point(const GridDev& g, const Segment& S, const Src& src, const Hit& h, uint64_t key,
+                                            uint64_t p0, uint32_t i) {
+  const unsigned long long li = atomicAdd(g.log_count, 1ull);
+  if (li < g.log_cap) {
+    uint32_t rgb[3];
+    src.colour(S, p0 + i, i, rgb);
+    uint32_t w[8];
+    point_words(S, h, rgb, w);
+    uint4* c4 = reinterpret_cast<uint4*>(g.log + li);
+    const unsigned long long gidx = S.scan_base + p0 + i;
+    c4[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), 0u, 0u);
+    c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
+    c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
+    c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
+  } else {
+    atomicOr(g.flags, kFlagLogOverflow);
+  }
+}
+
 // Warp-convergent: every lane calls it; m[j] says whether this lane's j-th point of the tile matches.
 // A point survives as a candidate iff its distance is <= the cell minimum seen so far; the true
 // winner (smallest distance, then smallest scan index == the strict `<` fold of :97-102) always is.
@@ -426,23 +447,8 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
       const double pz = reconstruct(h[j].z, S.scale[2], S.offset[2]);
       e[j] = grid_eval(g, px, py, pz);
       if (e[j].aliased || alias_find(g, e[j].key) != ~0u) {
-        // a point of an affected key: logged for the ordered replay, never enters the table (rare path)
-        const unsigned long long li = atomicAdd(g.log_count, 1ull);
-        if (li < g.log_cap) {
-          const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
-          uint32_t rgb[3];
-          src.colour(S, p0 + i, i, rgb);
-          uint32_t w[8];
-          point_words(S, h[j], rgb, w);
-          uint4* c4 = reinterpret_cast<uint4*>(g.log + li);
-          const unsigned long long gidx = S.scan_base + p0 + i;
-          c4[0] = make_uint4((uint32_t)e[j].key, (uint32_t)(e[j].key >> 32), 0u, 0u);
-          c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
-          c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
-          c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
-        } else {
-          atomicOr(g.flags, kFlagLogOverflow);
-        }
+        // a point of an affected key: logged for the ordered replay, never enters the table
+        grid_log_point(g, S, src, h[j], e[j].key, p0, (uint32_t)j * kBlock + threadIdx.x);
       } else if (!g.log_only) {
         slot[j] = grid_slot(g, e[j].key, true);
         if (slot[j] == ~0ull)
