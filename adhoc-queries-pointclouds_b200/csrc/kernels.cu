@@ -1344,6 +1344,7 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
   // ---------------- consumer warps ----------------
   const uint32_t w = warp_id();
   uint32_t emit_next = 0, counted = 0;
+  bool dense = false;  // more than three quarters of the warp's records of the latest unit matched
   auto emit_one = [&]() {
     const uint32_t pb = emit_next % kSelBufs;
     mbar_wait(&bar_pre[pb], (emit_next / kSelBufs) & 1u);
@@ -1399,9 +1400,14 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
         mbar_arrive(&bar_sfree[slot]);
         select_post_count<kSelRWarps>(P, U, cnt, &bar_cnt[b]);
       }
+      dense = cnt * 4u > 3u * (uint32_t)WPTS;
     }
     counted = n + 1u;
-    while (emit_next + (uint32_t)kSelLag < counted) emit_one();
+    // Dense matches: the emit is what the warp spends its time on, so look-backs resolve in its shadow anyway —
+    // emit close behind the front, while the matching records are still in L2.  Sparse matches: stay three units
+    // behind, so that the warp never waits for a look-back.
+    const uint32_t lag = dense ? 1u : (uint32_t)kSelLag;
+    while (emit_next + lag < counted) emit_one();
   }
   while (emit_next < counted) emit_one();
 }
