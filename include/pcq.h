@@ -39,9 +39,12 @@ extern "C" {
  *                PCQ_ERR_PANIC   ~ a place where the reference panics (AABB::from_min_max with
  *                                  min > max: las.rs:61, 88; last.rs:55, 98; main.rs:80),
  *                PCQ_ERR_GRID    ~ SparseGrid::new's "Too many cells" error (grid_sampling.rs:32-34),
- *                PCQ_ERR_ALIASED ~ density insert hit the key-aliasing case whose result depends on
- *                                  insertion order (grid_sampling.rs:62-70 vs 78-82) and the
- *                                  collector was created without replay support.
+ *                PCQ_ERR_ALIASED ~ no counterpart in the reference.  SparseGrid keys that suffer key aliasing
+ *                                  (grid_sampling.rs:62-70 vs 78-82: the result for such a key is a sequential
+ *                                  fold in scan order) are replayed exactly on one GPU; the code is returned
+ *                                  where that order cannot be honoured: merging such collectors across GPUs
+ *                                  (pcq_grid_export_candidates), point ranges fed out of scan order, or a hashed
+ *                                  table that must be re-hashed in the launch that meets the aliased key.
  * ---------------------------------------------------------------------------------------------- */
 enum pcq_status {
   PCQ_OK = 0,
