@@ -169,6 +169,29 @@ def test_last_class_select_multi_unit(pcq, ctx):
     assert same_point_seq(c.points(), want[0].points())
 
 
+@pytest.mark.parametrize("layout,fmt,unit", [("las", 0, 4096), ("las", 1, 3072), ("las", 2, 3072), ("las", 3, 2048),
+                                             ("last", 1, 7168), ("last", 3, 7168)])
+def test_select_around_unit_boundaries(pcq, ctx, layout, fmt, unit):
+    """file sizes just below / at / above multiples of the look-back unit of k_select_ring (and of k_select's 2048),
+    sparse and dense boxes, every file its own collector and all files in one collector"""
+    rng = np.random.default_rng(unit + fmt)
+    sizes = [unit - 1, unit, unit + 1, 2 * unit + 17, 3 * unit - 1, 2047, 2049, 5 * unit]
+    files = [random_file(rng, n, fmt, layout, fmt % 2) for n in sizes]
+    exts = [layout] * len(files)
+    for lo, hi in ((100, 90_000), (40_000, 60_000), (-60_000, 160_000)):  # ~60 %, ~1 %, everything
+        b = box(fmt % 2, lo, hi)  # (isotropic headers: the x-scale quirk would turn these boxes inside out)
+        for per_file in (False, True):
+            want = oracle_run(files, exts, orc.COLLECT_BUFFER, bounds=b, per_file=per_file)
+            for variant in (2, 1):
+                ctx.set_scan_variant(variant)
+                got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_BUFFER, bounds=b, per_file=per_file)
+                assert_same(orc.COLLECT_BUFFER, got, want)
+    ctx.set_scan_variant(0)
+    want = oracle_run(files, exts, orc.COLLECT_BUFFER, cls=2)
+    got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_BUFFER, cls=2)
+    assert_same(orc.COLLECT_BUFFER, got, want)
+
+
 def test_odd_record_lengths_and_extended_formats(pcq, ctx):
     rng = np.random.default_rng(5)
     for fmt, rl, ver in ((0, 23, (1, 2)), (1, 31, (1, 2)), (2, 29, (1, 2)), (3, 40, (1, 3)), (6, 30, (1, 4)), (7, 36, (1, 4))):
