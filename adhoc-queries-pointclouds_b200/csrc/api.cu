@@ -72,9 +72,7 @@ struct pcq_ctx {
   // MODE_SELECT scratch
   unsigned long long* tile_state = nullptr;  // [0] = ticket, [1..] = descriptors
   uint64_t tile_state_cap = 0;
-  // GRID finalisation scratch (one finalisation at a time)
-  unsigned long long* idx_scratch = nullptr;
-  uint64_t idx_scratch_cap = 0;
+  // GRID export scratch (one export at a time)
   unsigned long long* part_scratch = nullptr;  // 2 * n_parts counters
   uint32_t part_scratch_cap = 0;
   // host-staged streaming
@@ -115,6 +113,7 @@ struct pcq_collector {
   uint8_t* d_final = nullptr;
   uint64_t final_cap = 0, final_n = 0;
   bool final_valid = false;
+  bool table_holds_winners = false;  // finalised in place: the cells of the winners hold scan indices until grid_restore
   // key-aliasing replay (alias.cu): affected keys in ordinal order, their fold states (host copy is authoritative
   // between launches), the device-side set and the replay log
   std::vector<uint64_t> akeys;
@@ -309,6 +308,18 @@ GridDev grid_view(const pcq_collector* c) {
   return g;
 }
 
+// a finalisation leaves the winners' scan indices in the table; before anything reads or updates distances again
+// the finalists write theirs back (phase 3 of k_grid_final_phase)
+int grid_restore(pcq_collector* c) {
+  if (!c->table_holds_winners) return PCQ_OK;
+  GridDev g = grid_view(c);
+  if (launch_grid_final_phase(g, c->cand_len, 3, c->ctx->sm_count, c->ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_final_phase launch failed");
+  c->ctx->launches++;
+  c->table_holds_winners = false;
+  return PCQ_OK;
+}
+
 int grow_log(pcq_collector* c, uint64_t need) {
   if (c->log_cap >= need) return PCQ_OK;
   CU(cudaStreamSynchronize(c->ctx->stream));
@@ -394,6 +405,7 @@ int grow_cands(pcq_collector* c, uint64_t need) {
 // drop candidates that no longer hold their cell's minimum; compacts in place through a scratch arena
 int prune_cands(pcq_collector* c) {
   pcq_ctx* ctx = c->ctx;
+  RC(grid_restore(c));
   c->prune_epoch++;
   if (c->cand_len == 0) return PCQ_OK;
   Candidate* tmp = nullptr;
@@ -483,6 +495,7 @@ int rehash_grid(pcq_collector* c) {
 int grid_finalize(pcq_collector* c) {
   if (c->final_valid) return PCQ_OK;
   pcq_ctx* ctx = c->ctx;
+  RC(grid_restore(c));
   const uint64_t n = c->cand_len;
   // winners of affected keys come from the ordered replay, not from the table
   std::vector<uint8_t> replayed;
@@ -503,25 +516,15 @@ int grid_finalize(pcq_collector* c) {
   }
   uint64_t from_table = 0;
   if (n) {
-    if (ctx->idx_scratch_cap < c->grid.table_slots) {
-      if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
-      ctx->idx_scratch = nullptr;
-      ctx->idx_scratch_cap = 0;
-      if (cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(PCQ_ERR_NOMEM, "cannot allocate density index table");
-      }
-      ctx->idx_scratch_cap = c->grid.table_slots;
-    }
-    CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
     CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
     GridDev g = grid_view(c);
-    if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0)
-      return fail(PCQ_ERR_CUDA, "k_grid_min_index launch failed");
-    if (launch_grid_emit(g, n, ctx->idx_scratch, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count,
-                         ctx->sm_count, ctx->stream) != 0)
+    for (int phase = 0; phase < 3; ++phase)
+      if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0)
+        return fail(PCQ_ERR_CUDA, "k_grid_final_phase launch failed");
+    if (launch_grid_emit(g, n, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count, ctx->sm_count, ctx->stream) != 0)
       return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
-    ctx->launches += 2;
+    c->table_holds_winners = true;  // the distances go back lazily (grid_restore): usually nothing follows
+    ctx->launches += 4;
     DevBlock b;
     RC(read_devblock(c, &b));
     from_table = b.out_count;
@@ -680,6 +683,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       if (lane_points[l] == 0) continue;
+      RC(grid_restore(c));
       const uint64_t slack = (uint64_t)ctx->sm_count * kGridCtasPerSm * (kBlock / 32) * kCandChunk;
       const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16) + slack;
       // Candidates are only ever dropped BETWEEN launches: what survives is every cell's current winner, which is
@@ -874,7 +878,6 @@ static void ctx_free(pcq_ctx* ctx) {
     if (s.ev) cudaEventDestroy(s.ev);
   }
   if (ctx->tile_state) cudaFree(ctx->tile_state);
-  if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
   if (ctx->part_scratch) cudaFree(ctx->part_scratch);
   for (int i = 0; i < kChunkBuffers; ++i) {
     if (ctx->chunk[i]) cudaFree(ctx->chunk[i]);
@@ -1132,6 +1135,7 @@ int pcq_collector_reset(pcq_collector* c) {
   c->out_len = 0;
   c->cand_len = 0;
   c->final_valid = false;
+  c->table_holds_winners = false;  // (the table is cleared below)
   c->final_n = 0;
   c->akeys.clear();
   c->astates.clear();
@@ -1443,27 +1447,20 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
                 c->akeys.size());
   const uint64_t n = c->cand_len;
   if (n == 0) return PCQ_OK;
-  if (ctx->idx_scratch_cap < c->grid.table_slots) {
-    if (ctx->idx_scratch) cudaFree(ctx->idx_scratch);
-    ctx->idx_scratch = nullptr;
-    ctx->idx_scratch_cap = 0;
-    CU(cudaMalloc(&ctx->idx_scratch, c->grid.table_slots * 8ull));
-    ctx->idx_scratch_cap = c->grid.table_slots;
-  }
+  RC(grid_restore(c));
   if (ctx->part_scratch_cap < n_parts) {
     if (ctx->part_scratch) cudaFree(ctx->part_scratch);
     ctx->part_scratch = nullptr;
     CU(cudaMalloc(&ctx->part_scratch, 2ull * n_parts * sizeof(unsigned long long)));
     ctx->part_scratch_cap = n_parts;
   }
-  CU(cudaMemsetAsync(ctx->idx_scratch, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
   CU(cudaMemsetAsync(ctx->part_scratch, 0, 2ull * n_parts * sizeof(unsigned long long), ctx->stream));
   GridDev g = grid_view(c);
-  if (launch_grid_min_index(g, n, ctx->idx_scratch, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");
-  if (launch_grid_emit(g, n, ctx->idx_scratch, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr,
-                       ctx->sm_count, ctx->stream) != 0)
+  for (int phase = 0; phase < 3; ++phase)
+    if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");
+  if (launch_grid_emit(g, n, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
     return fail(PCQ_ERR_CUDA, "launch failed");
-  ctx->launches += 2;
+  ctx->launches += 4;
   std::vector<unsigned long long> h(n_parts);
   CU(cudaMemcpyAsync(h.data(), ctx->part_scratch, n_parts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1483,10 +1480,11 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
   }
   CU(cudaMemcpyAsync(ctx->part_scratch + n_parts, cursor.data(), n_parts * sizeof(unsigned long long),
                      cudaMemcpyHostToDevice, ctx->stream));
-  if (launch_grid_emit(g, n, ctx->idx_scratch, 1, n_parts, ctx->part_scratch, ctx->part_scratch + n_parts, c->d_export,
-                       nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
+  if (launch_grid_emit(g, n, 1, n_parts, ctx->part_scratch, ctx->part_scratch + n_parts, c->d_export, nullptr, nullptr,
+                       ctx->sm_count, ctx->stream) != 0)
     return fail(PCQ_ERR_CUDA, "launch failed");
-  ctx->launches++;
+  if (launch_grid_final_phase(g, n, 3, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");  // distances back
+  ctx->launches += 2;
   CU(cudaStreamSynchronize(ctx->stream));
   *out_dev_candidates = c->d_export;
   return PCQ_OK;
@@ -1499,6 +1497,7 @@ int pcq_grid_import_candidates(pcq_collector* c, const void* dev_candidates, uin
   if (!dev_candidates) return fail(PCQ_ERR_ARG, "null candidates");
   pcq_ctx* ctx = c->ctx;
   RC(use_device(ctx));
+  RC(grid_restore(c));
   c->final_valid = false;
   for (int attempt = 0; attempt < 8; ++attempt) {
     RC(grow_cands(c, c->cand_len + n));

@@ -1621,41 +1621,61 @@ __global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned 
   }
 }
 
-// among the candidates at their cell's minimum distance, the smallest scan index wins
-__global__ void k_grid_min_index(GridDev g, uint64_t n, unsigned long long* idx_table) {
+// Finalisation (HashMap::values, grid_sampling.rs:111-113) works IN PLACE: the distance table doubles as the
+// per-cell "smallest scan index among the candidates at the minimum distance" table, so a 2^27-cell grid needs no
+// second 1 GB array (and no 1 GB memset per finalisation).  One launch per phase, all over the candidate arena:
+//   phase 0  flag the candidates that sit at their cell's minimum distance ("finalists"; byte 55 of the candidate)
+//   phase 1  finalists clear their cell:                table[slot] = ~0
+//   phase 2  the smallest scan index wins:              atomicMin(table[slot], scan index)
+//   emit     k_grid_emit (winner == finalist whose scan index is in the table)
+//   phase 3  finalists put the distance back:           table[slot] = dist bits   (the collector can go on collecting)
+__global__ void k_grid_final_phase(GridDev g, uint64_t n, int phase) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const Candidate& c = g.cands[i];
-    if (c.scan_idx == kCandEmpty || alias_find(g, c.key) != ~0u) continue;  // affected keys come from the replay
+    Candidate& c = g.cands[i];
+    if (c.scan_idx == kCandEmpty) continue;
+    if (phase == 0) {
+      bool fin = false;
+      if (alias_find(g, c.key) == ~0u) {  // affected keys come from the replay
+        const uint64_t slot = grid_slot(g, c.key, false);
+        fin = slot != ~0ull && g.table[slot] == c.dist_bits;
+      }
+      c.pad_[0] = fin ? 1 : 0;
+      continue;
+    }
+    if (!c.pad_[0]) continue;
     const uint64_t slot = grid_slot(g, c.key, false);
-    if (slot != ~0ull && g.table[slot] == c.dist_bits) atomicMin(idx_table + slot, (unsigned long long)c.scan_idx);
+    if (phase == 1)
+      g.table[slot] = ~0ull;
+    else if (phase == 2)
+      atomicMin(g.table + slot, (unsigned long long)c.scan_idx);
+    else
+      g.table[slot] = c.dist_bits;
   }
 }
 
 // winners -> 31-byte records (order arbitrary, like HashMap::values) or -> per-owner candidate parts
 // mode 0: count per part, mode 1: write candidates into parts, mode 2: write 31-byte points
-__global__ void k_grid_emit(GridDev g, uint64_t n, unsigned long long* idx_table, int mode, uint32_t n_parts,
-                            unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
-                            uint8_t* out_points, unsigned long long* out_count) {
+// (between phase 2 and phase 3 of the finalisation: table[slot] holds the winning scan index)
+__global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
+                            unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points,
+                            unsigned long long* out_count) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
-    if (c.scan_idx == kCandEmpty || alias_find(g, c.key) != ~0u) continue;
+    if (c.scan_idx == kCandEmpty || !c.pad_[0]) continue;
     const uint64_t slot = grid_slot(g, c.key, false);
-    if (slot == ~0ull || g.table[slot] != c.dist_bits) continue;
+    unsigned long long* cell = g.table + slot;
+    const unsigned long long mine = (unsigned long long)c.scan_idx, claimed = mine | (1ull << 63);
     if (mode == 0) {
       // count the winner once even if the candidate list holds duplicates of it
-      if (idx_table[slot] != c.scan_idx) continue;
-      if (atomicCAS(idx_table + slot, (unsigned long long)c.scan_idx, (unsigned long long)c.scan_idx | (1ull << 63)) !=
-          (unsigned long long)c.scan_idx)
-        continue;
+      if (*cell != mine) continue;
+      if (atomicCAS(cell, mine, claimed) != mine) continue;
       atomicAdd(part_counts + (uint32_t)(mix64(c.key) % n_parts), 1ull);
     } else if (mode == 1) {
       // second walk after mode 0: claimed entries carry bit 63; release the claim while emitting
-      if (idx_table[slot] != ((unsigned long long)c.scan_idx | (1ull << 63))) continue;
-      if (atomicCAS(idx_table + slot, (unsigned long long)c.scan_idx | (1ull << 63), (unsigned long long)c.scan_idx) !=
-          ((unsigned long long)c.scan_idx | (1ull << 63)))
-        continue;
+      if (*cell != claimed) continue;
+      if (atomicCAS(cell, claimed, mine) != claimed) continue;
       const uint32_t part = (uint32_t)(mix64(c.key) % n_parts);
       const unsigned long long o = atomicAdd(part_cursor + part, 1ull);
       const uint4* s4 = reinterpret_cast<const uint4*>(&c);
@@ -1665,10 +1685,8 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, unsigned long long* idx_table
       o4[2] = s4[2];
       o4[3] = s4[3];
     } else {
-      if (idx_table[slot] != c.scan_idx) continue;
-      if (atomicCAS(idx_table + slot, (unsigned long long)c.scan_idx, (unsigned long long)c.scan_idx | (1ull << 63)) !=
-          (unsigned long long)c.scan_idx)
-        continue;
+      if (*cell != mine) continue;
+      if (atomicCAS(cell, mine, claimed) != mine) continue;
       const unsigned long long o = atomicAdd(out_count, 1ull);
       uint8_t* dst = out_points + o * 31ull;
 #pragma unroll
@@ -1892,18 +1910,18 @@ int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned 
   return check_launch();
 }
 
-int launch_grid_min_index(const GridDev& g, uint64_t n, unsigned long long* idx_table, int sm_count, void* stream) {
+int launch_grid_final_phase(const GridDev& g, uint64_t n, int phase, int sm_count, void* stream) {
   if (n == 0) return 0;
-  k_grid_min_index<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, idx_table);
+  k_grid_final_phase<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, phase);
   return check_launch();
 }
 
-int launch_grid_emit(const GridDev& g, uint64_t n, unsigned long long* idx_table, int mode, uint32_t n_parts,
-                     unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
-                     uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream) {
+int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
+                     unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points, unsigned long long* out_count,
+                     int sm_count, void* stream) {
   if (n == 0) return 0;
-  k_grid_emit<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, idx_table, mode, n_parts, part_counts,
-                                                                         part_cursor, out_cands, out_points, out_count);
+  k_grid_emit<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, mode, n_parts, part_counts, part_cursor, out_cands,
+                                                                         out_points, out_count);
   return check_launch();
 }
 

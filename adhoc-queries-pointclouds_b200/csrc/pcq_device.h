@@ -143,11 +143,13 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
 int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count, int sm_count,
                       void* stream);
-int launch_grid_min_index(const GridDev& g, uint64_t n, unsigned long long* idx_table, int sm_count, void* stream);
+// in-place finalisation of a density table (kernels.cu): phase 0 flag finalists, 1 clear their cells, 2 smallest scan
+// index wins, [launch_grid_emit], 3 put the distances back
+int launch_grid_final_phase(const GridDev& g, uint64_t n, int phase, int sm_count, void* stream);
 // mode 0: count winners per owner part, 1: write winners as candidates into their parts, 2: write 31-byte points
-int launch_grid_emit(const GridDev& g, uint64_t n, unsigned long long* idx_table, int mode, uint32_t n_parts,
-                     unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
-                     uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream);
+int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
+                     unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points, unsigned long long* out_count,
+                     int sm_count, void* stream);
 int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream);
 
 // alias replay (alias.cu).  All asynchronous on `stream` unless stated otherwise.
