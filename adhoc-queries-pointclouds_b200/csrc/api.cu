@@ -732,7 +732,9 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     P.sel_ring = (mode == MODE_SELECT && variant == 2 && !select_bytes) ? R : 0u;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
     if (mode == MODE_SELECT) {
+#ifdef PCQ_DEBUG_HOOKS
       if (const char* e = std::getenv("PCQ_SELECT_DEBUG")) P.debug = (uint32_t)std::atoi(e);
+#endif
       RC(ensure_tile_state(ctx, n_tiles));
       P.ticket = ctx->tile_state;
       P.tile_state = ctx->tile_state + kDescStride;

@@ -29,6 +29,15 @@
 #include "pcq_device.h"
 #include "grid_math.cuh"
 
+// Measurement hooks of the select kernels (skip the look-back / the emit: results are WRONG).  Compiled out unless the
+// library is built with -DPCQ_DEBUG_HOOKS (make EXTRA=-DPCQ_DEBUG_HOOKS); tools/dbg_select.sh then drives them through
+// PCQ_SELECT_DEBUG.
+#ifdef PCQ_DEBUG_HOOKS
+#define PCQ_HOOK(P, bit) (((P).debug & (bit)) != 0u)
+#else
+#define PCQ_HOOK(P, bit) false
+#endif
+
 namespace pcq {
 
 // ------------------------------------------------------------------------------------------------
@@ -1074,7 +1083,7 @@ __device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUni
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     // (the unit's aggregate was published by the consumer warp that posted the last count)
     unsigned long long excl = 0;
-    if (tile != lane_first && !(P.debug & 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
+    if (tile != lane_first && !PCQ_HOOK(P, 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
     if (ln == 0) {
       if (tile != lane_first) st_state(P.tile_state + tile * kDescStride, (kStPrefix << kStatusShift) | (excl + (unsigned long long)total));
       U.out_rec = U.out_base + excl;
@@ -1216,10 +1225,10 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
       const bool must = !nxt || emit_next + (uint32_t)kSelLag < counted;
       if (must) {
         mbar_wait(&bar_pre[pb], par);
-      } else if (!(P.debug & 4u) || !mbar_test(&bar_pre[pb], par)) {
+      } else if (!PCQ_HOOK(P, 4u) || !mbar_test(&bar_pre[pb], par)) {
         break;  // (debug 4: emit a younger unit early when its prefix is already there)
       }
-      if (!(P.debug & 2u)) {
+      if (!PCQ_HOOK(P, 2u)) {
         const uint16_t* list = match_list[w][emit_next % (uint32_t)(kSelLag + 1)];
         select_emit_warp<AL>(unit[pb], [list](uint32_t r) { return (uint32_t)list[r]; }, (uint32_t)kSelWarpPts, stage[w]);
       }
@@ -1348,7 +1357,7 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
   auto emit_one = [&]() {
     const uint32_t pb = emit_next % kSelBufs;
     mbar_wait(&bar_pre[pb], (emit_next / kSelBufs) & 1u);
-    if (!(P.debug & 2u)) {
+    if (!PCQ_HOOK(P, 2u)) {
       const uint32_t* bal = m_bal[w][emit_next % (uint32_t)(kSelLag + 1)];
       const uint16_t* run = m_run[w][emit_next % (uint32_t)(kSelLag + 1)];
       auto index_of = [bal, run](uint32_t r) -> uint32_t {
@@ -1509,7 +1518,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
       const uint32_t par = (emit_next / kSelBufs) & 1u;
       if (nxt && emit_next + (uint32_t)kSelBLag >= counted) break;
       mbar_wait(&bar_pre[pb], par);
-      if (!(P.debug & 2u)) {
+      if (!PCQ_HOOK(P, 2u)) {
         const uint16_t* mk = m_mask[w][emit_next % (uint32_t)(kSelBLag + 1)];
         const uint16_t* pr = m_pre[w][emit_next % (uint32_t)(kSelBLag + 1)];
         auto index_of = [mk, pr](uint32_t r) -> uint32_t {

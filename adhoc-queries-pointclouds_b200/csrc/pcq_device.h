@@ -131,7 +131,7 @@ struct ScanParams {
   unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
   uint32_t sel_bytes;              // MODE_SELECT: 1 = k_select_bytes (LAST class query, 32768-point units)
   uint32_t sel_ring;               // MODE_SELECT: record length when the launch qualifies for k_select_ring, else 0
-  uint32_t debug;                  // measurement only (PCQ_SELECT_DEBUG): 1 = skip the look-back, 2 = skip the emit
+  uint32_t debug;                  // measurement hooks, only in -DPCQ_DEBUG_HOOKS builds: 1 = skip the look-back, 2 = skip the emit
 };
 
 // launch wrappers implemented in kernels.cu (stream is a cudaStream_t); 0 = ok, < 0 = CUDA error
