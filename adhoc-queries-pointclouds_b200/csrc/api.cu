@@ -630,8 +630,23 @@ int alias_slow_path(pcq_ctx* ctx, const std::vector<Segment>& segs, ScanParams P
 }
 
 // one kernel launch for a prepared batch of segments; handles BUFFER / GRID capacity retries
+// Share of a file's points a bounds query can be expected to match if points were spread evenly over the header box:
+// volume of (query box ∩ header box) / volume of the header box.  Only steers kernel choice (density insert: match
+// queue or direct), never results.  Class queries: unknown (-1).
+double expected_match_fraction(const pcq_file_desc& d, const pcq_query* q) {
+  if (q->kind != PCQ_QUERY_BOUNDS) return -1.0;
+  double f = 1.0;
+  for (int i = 0; i < 3; ++i) {
+    const double ext = d.hdr_max[i] - d.hdr_min[i];
+    if (!(ext > 0.0)) continue;  // flat or unusable header axis: no information
+    const double lo = std::max(q->qmin[i], d.hdr_min[i]), hi = std::min(q->qmax[i], d.hdr_max[i]);
+    f *= std::min(1.0, std::max(0.0, (hi - lo) / ext));
+  }
+  return f;
+}
+
 int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_collector* const* collectors,
-              uint32_t n_collectors, const std::vector<uint64_t>& lane_points) {
+              uint32_t n_collectors, const std::vector<uint64_t>& lane_points, double match_fraction = -1.0) {
   const int kind = collectors[0]->kind;
   if (segs.empty()) return PCQ_OK;
 
@@ -728,6 +743,9 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     P.n_tiles = n_tiles;
     P.tile_pts = tile_pts;
     P.sel_bytes = select_bytes ? 1u : 0u;
+    // density insert: a box that covers less than a quarter of the points' volume goes through the match queue
+    P.grid_sparse = (mode == MODE_GRID && match_fraction >= 0.0 && match_fraction < 0.25) ? 1u : 0u;
+    if (const char* e = std::getenv("PCQ_GRID_SPARSE")) P.grid_sparse = std::atoi(e) ? 1u : 0u;
     // uniform record length + 16-byte aligned ranges (staged_ok) and a predicate that lives in the staged records
     P.sel_ring = (mode == MODE_SELECT && variant == 2 && !select_bytes) ? R : 0u;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
@@ -1236,6 +1254,8 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
   std::vector<Segment> segs;
   segs.reserve(n_files);
   std::vector<uint64_t> lane_points(n_collectors, 0);
+  bool frac_known = true;
+  double frac_pts = 0.0, all_pts = 0.0;
   for (uint32_t i = 0; i < n_files; ++i) {
     pcq_file* f = files[i];
     if (!f) return fail(PCQ_ERR_ARG, "null file %u", i);
@@ -1251,8 +1271,13 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base, query->kind);
     lane_points[lane] += f->n_points;
     segs.push_back(s);
+    const double fr = expected_match_fraction(f->desc, query);
+    if (fr < 0.0) frac_known = false;
+    frac_pts += (fr < 0.0 ? 0.0 : fr) * (double)f->n_points;
+    all_pts += (double)f->n_points;
   }
-  return run_batch(ctx, segs, query, collectors, n_collectors, lane_points);
+  return run_batch(ctx, segs, query, collectors, n_collectors, lane_points,
+                   frac_known && all_pts > 0.0 ? frac_pts / all_pts : -1.0);
 }
 
 int pcq_host_alloc(size_t n_bytes, void** out) {
@@ -1419,7 +1444,8 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       std::fill(lane_points.begin(), lane_points.end(), 0);
       lane_points[fp.lane] = pc.n;
       // run_batch indexes lanes by Segment::lane, so hand it the query's full collector array
-      RC(run_batch(ctx, segs, queries + q, collectors + (size_t)q * n_collectors, n_collectors, lane_points));
+      RC(run_batch(ctx, segs, queries + q, collectors + (size_t)q * n_collectors, n_collectors, lane_points,
+                   expected_match_fraction(fp.d, queries + q)));
     }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }

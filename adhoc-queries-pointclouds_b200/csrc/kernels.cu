@@ -407,18 +407,67 @@ __device__ __forceinline__ unsigned long long cand_reserve(const GridDev& g, Can
   return r;
 }
 
-// rare path, kept out of line so that it costs the insert kernel neither registers nor instruction-cache space
+// One queued match of the sparse density insert (see process_tile): everything the insert needs, so that the tile the
+// point came from can be released.
+struct alignas(16) GridQEntry {
+  int32_t x, y, z;
+  uint32_t rg;   // r | g << 16
+  uint32_t bc;   // b | cls << 16
+  uint32_t pad_;
+  unsigned long long gidx;  // collector-wide scan index
+};
+
+// Where the kPPT points of a lane come from: straight from the tile ...
 template <class Src>
-__device__ __noinline__ void grid_log_point(const GridDev& g, const Segment& S, const Src& src, const Hit& h, uint64_t key,
-                                            uint64_t p0, uint32_t i) {
-  const unsigned long long li = atomicAdd(g.log_count, 1ull);
-  if (li < g.log_cap) {
+struct TileFetch {
+  const Src& src;
+  const Hit (&h)[kPPT];
+  uint64_t p0;
+  __device__ __forceinline__ void xyz(int j, int32_t& x, int32_t& y, int32_t& z) const {
+    x = h[j].x;
+    y = h[j].y;
+    z = h[j].z;
+  }
+  __device__ __forceinline__ void words(const Segment& S, int j, uint32_t w[8]) const {
+    const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
     uint32_t rgb[3];
     src.colour(S, p0 + i, i, rgb);
-    uint32_t w[8];
+    point_words(S, h[j], rgb, w);
+  }
+  __device__ __forceinline__ unsigned long long gidx(const Segment& S, int j) const {
+    return S.scan_base + p0 + (uint32_t)j * kBlock + threadIdx.x;
+  }
+};
+// ... or from the CTA's match queue (entries stay in shared memory until the flush ends)
+struct QueueFetch {
+  const GridQEntry* qe[kPPT];
+  __device__ __forceinline__ void xyz(int j, int32_t& x, int32_t& y, int32_t& z) const {
+    x = qe[j]->x;
+    y = qe[j]->y;
+    z = qe[j]->z;
+  }
+  __device__ __forceinline__ void words(const Segment& S, int j, uint32_t w[8]) const {
+    const GridQEntry& q = *qe[j];
+    Hit h;
+    h.x = q.x;
+    h.y = q.y;
+    h.z = q.z;
+    h.cls = q.bc >> 16;
+    const uint32_t rgb[3] = {q.rg & 0xFFFFu, q.rg >> 16, q.bc & 0xFFFFu};
     point_words(S, h, rgb, w);
+  }
+  __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return qe[j]->gidx; }
+};
+
+// rare path, kept out of line so that it costs the insert kernel neither registers nor instruction-cache space
+template <class Fetch>
+__device__ __noinline__ void grid_log_point(const GridDev& g, const Segment& S, const Fetch& f, int j, uint64_t key) {
+  const unsigned long long li = atomicAdd(g.log_count, 1ull);
+  if (li < g.log_cap) {
+    uint32_t w[8];
+    f.words(S, j, w);
     uint4* c4 = reinterpret_cast<uint4*>(g.log + li);
-    const unsigned long long gidx = S.scan_base + p0 + i;
+    const unsigned long long gidx = f.gidx(S, j);
     c4[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), 0u, 0u);
     c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
     c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
@@ -433,9 +482,9 @@ __device__ __noinline__ void grid_log_point(const GridDev& g, const Segment& S, 
 // winner (smallest distance, then smallest scan index == the strict `<` fold of :97-102) always is.
 // The kPPT points of a lane are taken through each step together so that their table reads (random
 // accesses into a table far larger than L2) are in flight at the same time.
-template <class Src>
-__device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment& S, const Src& src, const bool (&m)[kPPT],
-                                                 const Hit (&h)[kPPT], uint64_t p0, CandChunk& ch) {
+template <class Fetch>
+__device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment& S, const bool (&m)[kPPT], const Fetch& f,
+                                                 CandChunk& ch) {
   bool any_m = false;
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) any_m |= m[j];
@@ -451,13 +500,15 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
     e[j].dist_bits = 0;
     e[j].aliased = false;
     if (m[j]) {
-      const double px = reconstruct(h[j].x, S.scale[0], S.offset[0]);
-      const double py = reconstruct(h[j].y, S.scale[1], S.offset[1]);
-      const double pz = reconstruct(h[j].z, S.scale[2], S.offset[2]);
+      int32_t vx, vy, vz;
+      f.xyz(j, vx, vy, vz);
+      const double px = reconstruct(vx, S.scale[0], S.offset[0]);
+      const double py = reconstruct(vy, S.scale[1], S.offset[1]);
+      const double pz = reconstruct(vz, S.scale[2], S.offset[2]);
       e[j] = grid_eval(g, px, py, pz);
       if (e[j].aliased || alias_find(g, e[j].key) != ~0u) {
         // a point of an affected key: logged for the ordered replay, never enters the table
-        grid_log_point(g, S, src, h[j], e[j].key, p0, (uint32_t)j * kBlock + threadIdx.x);
+        grid_log_point(g, S, f, j, e[j].key);
       } else if (!g.log_only) {
         slot[j] = grid_slot(g, e[j].key, true);
         if (slot[j] == ~0ull)
@@ -493,13 +544,10 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
     if (want[j]) {
       const unsigned long long ci = base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u));
       if (ci < g.cand_cap) {
-        const uint32_t i = (uint32_t)j * kBlock + threadIdx.x;
-        uint32_t rgb[3];
-        src.colour(S, p0 + i, i, rgb);
         uint32_t w[8];
-        point_words(S, h[j], rgb, w);
+        f.words(S, j, w);
         uint4* c4 = reinterpret_cast<uint4*>(g.cands + ci);
-        const unsigned long long gidx = S.scan_base + p0 + i;
+        const unsigned long long gidx = f.gidx(S, j);
         c4[0] = make_uint4((uint32_t)e[j].key, (uint32_t)(e[j].key >> 32), (uint32_t)e[j].dist_bits, (uint32_t)(e[j].dist_bits >> 32));
         c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
         c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
@@ -526,10 +574,23 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
   return t;
 }
 
+// Match queue of the density insert (MODE_GRIDQ).  With a small query box only a few lanes of a warp carry a match,
+// yet the insert (three IEEE divisions, table read, atomic, candidate write) costs a warp the same whether 1 or 32
+// lanes take part — a 3 % box paid two thirds of the all-match price.  Matching points are queued in shared memory
+// as they are found and inserted kGridQFlush at a time with every lane busy; the queue is emptied before the CTA
+// moves to another segment and at the end.  Dense queries keep the direct path (MODE_GRID): the host picks per launch.
+constexpr uint32_t kGridQFlush = kBlock;                     // insert when at least this many matches are queued
+constexpr uint32_t kGridQCap = kGridQFlush - 1u + kTilePts;  // one more tile always fits
+
+struct GridQ {
+  GridQEntry* q;
+  uint32_t* n;
+};
+
 template <int MODE, class Src>
 __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment& S, uint64_t tile, const Src& src,
-                                             unsigned long long& acc, LaneChunk& ch) {
-  static_assert(MODE == MODE_COUNT || MODE == MODE_GRID, "select has its own kernels");
+                                             unsigned long long& acc, LaneChunk& ch, const GridQ& gq) {
+  static_assert(MODE == MODE_COUNT || MODE == MODE_GRID || MODE == MODE_GRIDQ, "select has its own kernels");
   const uint64_t p0 = (tile - S.first_tile) * (uint64_t)kTilePts;
   const uint64_t rem = S.n_points - p0;
   const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
@@ -547,15 +608,64 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment&
   if constexpr (MODE == MODE_COUNT) {
 #pragma unroll
     for (int j = 0; j < kPPT; ++j) acc += m[j] ? 1ull : 0ull;
-  } else {
+  } else if constexpr (MODE == MODE_GRID) {
     const GridDev& g = P.lanes[S.lane].grid;
     if (ch.lane != S.lane) {  // a warp's chunk belongs to one collector's arena
       if (ch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[ch.lane].grid, ch.c);
       ch.c = CandChunk();
       ch.lane = S.lane;
     }
-    grid_insert_tile(g, S, src, m, h, p0, ch.c);
+    grid_insert_tile(g, S, m, TileFetch<Src>{src, h, p0}, ch.c);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPPT; ++j) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, m[j]);
+      if (bal == 0u) continue;
+      uint32_t base = 0;
+      if (lane_id() == 0) base = atomicAdd(gq.n, (uint32_t)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (m[j]) {
+        const uint32_t i = (uint32_t)j * kBlock + tid;
+        uint32_t rgb[3];
+        src.colour(S, p0 + i, i, rgb);
+        GridQEntry& e = gq.q[base + (uint32_t)__popc(bal & ((1u << lane_id()) - 1u))];
+        e.x = h[j].x;
+        e.y = h[j].y;
+        e.z = h[j].z;
+        e.rg = (rgb[0] & 0xFFFFu) | (rgb[1] << 16);
+        e.bc = (rgb[2] & 0xFFFFu) | ((h[j].cls & 0xFFu) << 16);
+        e.gidx = S.scan_base + p0 + i;
+      }
+    }
   }
+}
+
+// MODE_GRIDQ: insert everything that is queued (all threads of the CTA; S is the segment the queued points belong to)
+__device__ __forceinline__ void grid_flush(const ScanParams& P, const Segment& S, const GridQ& gq, LaneChunk& ch) {
+  __syncthreads();  // every queued entry is written
+  const uint32_t n = *gq.n;
+  if (n != 0u) {
+    const GridDev& g = P.lanes[S.lane].grid;
+    if (ch.lane != S.lane) {
+      if (ch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[ch.lane].grid, ch.c);
+      ch.c = CandChunk();
+      ch.lane = S.lane;
+    }
+    for (uint32_t base = 0; base < n; base += kBlock * kPPT) {
+      bool m[kPPT];
+      QueueFetch f;
+#pragma unroll
+      for (int j = 0; j < kPPT; ++j) {
+        const uint32_t e = base + (uint32_t)j * kBlock + threadIdx.x;
+        m[j] = e < n;
+        f.qe[j] = gq.q + (m[j] ? e : 0u);
+      }
+      grid_insert_tile(g, S, m, f, ch.c);
+    }
+  }
+  __syncthreads();  // every entry is consumed
+  if (threadIdx.x == 0) *gq.n = 0u;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,6 +675,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
   __shared__ Segment sseg;
   __shared__ unsigned long long s_red[kBlock / 32];
+  __shared__ GridQEntry s_q[MODE == MODE_GRIDQ ? kGridQCap : 1];
+  __shared__ uint32_t s_qn;
+  const GridQ gq{s_q, &s_qn};
+  if (threadIdx.x == 0) s_qn = 0u;
+  __syncthreads();
 
   uint32_t seg_i = 0xFFFFFFFFu;
   uint32_t seg_cursor = 0;
@@ -585,6 +700,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
           acc = 0;
         }
       }
+      if constexpr (MODE == MODE_GRIDQ) {
+        if (seg_i != 0xFFFFFFFFu) grid_flush(P, sseg, gq, lch);
+      }
       __syncthreads();
       const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_cursor);
       uint32_t* dstw = reinterpret_cast<uint32_t*>(&sseg);
@@ -592,7 +710,11 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
       seg_i = seg_cursor;
       __syncthreads();
     }
-    process_tile<MODE>(P, sseg, tile, src, acc, lch);
+    process_tile<MODE>(P, sseg, tile, src, acc, lch, gq);
+    if constexpr (MODE == MODE_GRIDQ) {
+      __syncthreads();
+      if (s_qn >= kGridQFlush) grid_flush(P, sseg, gq, lch);
+    }
   }
   if constexpr (MODE == MODE_COUNT) {
     if (seg_i != 0xFFFFFFFFu) {
@@ -600,7 +722,10 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
       if (threadIdx.x == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
     }
   }
-  if constexpr (MODE == MODE_GRID) {
+  if constexpr (MODE == MODE_GRIDQ) {
+    if (seg_i != 0xFFFFFFFFu) grid_flush(P, sseg, gq, lch);
+  }
+  if constexpr (MODE == MODE_GRID || MODE == MODE_GRIDQ) {
     if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
   }
 }
@@ -666,7 +791,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
   const uint32_t tid = threadIdx.x;
   // producer state (meaningful in thread 0 only)
   uint64_t stream_policy = 0;
-  if constexpr (MODE == MODE_GRID) {
+  if constexpr (MODE == MODE_GRID || MODE == MODE_GRIDQ) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
   }
   uint32_t prod_seg = 0;
@@ -688,7 +813,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
     stage_tile[s] = tile;
     stage_seg[s] = prod_seg;
     mbar_arrive_expect_tx(&full_bar[s], bytes);
-    if constexpr (MODE == MODE_GRID)
+    if constexpr (MODE == MODE_GRID || MODE == MODE_GRIDQ)
       bulk_copy_g2s_hint(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s], stream_policy);
     else
       bulk_copy_g2s(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s]);
@@ -704,6 +829,12 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 #pragma unroll 1
     for (int s = 0; s < STAGES; ++s) produce(s);
   }
+  __syncthreads();
+
+  __shared__ GridQEntry s_q[MODE == MODE_GRIDQ ? kGridQCap : 1];
+  __shared__ uint32_t s_qn;
+  const GridQ gq{s_q, &s_qn};
+  if (tid == 0) s_qn = 0u;
   __syncthreads();
 
   uint32_t seg_i = 0xFFFFFFFFu;
@@ -722,6 +853,9 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
           if (tid == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
           acc = 0;
         }
+      }
+      if constexpr (MODE == MODE_GRIDQ) {
+        if (seg_i != 0xFFFFFFFFu) grid_flush(P, sseg, gq, lch);
       }
       __syncthreads();
       const uint32_t* srcw = reinterpret_cast<const uint32_t*>(P.segs + seg_now);
@@ -751,10 +885,13 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
       acc += n;
     } else {
       SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
-      process_tile<MODE>(P, sseg, tile, src, acc, lch);
+      process_tile<MODE>(P, sseg, tile, src, acc, lch, gq);
     }
     __syncthreads();  // every thread is done reading stage s
     if (tid == 0) produce((int)s);
+    if constexpr (MODE == MODE_GRIDQ) {
+      if (s_qn >= kGridQFlush) grid_flush(P, sseg, gq, lch);  // (the barrier above ordered the queue counter)
+    }
   }
   if constexpr (MODE == MODE_COUNT) {
     if (seg_i != 0xFFFFFFFFu) {
@@ -762,7 +899,10 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
       if (tid == 0 && t) atomicAdd(P.lanes[sseg.lane].count, t);
     }
   }
-  if constexpr (MODE == MODE_GRID) {
+  if constexpr (MODE == MODE_GRIDQ) {
+    if (seg_i != 0xFFFFFFFFu) grid_flush(P, sseg, gq, lch);
+  }
+  if constexpr (MODE == MODE_GRID || MODE == MODE_GRIDQ) {
     if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
   }
 }
@@ -1772,7 +1912,7 @@ static int persistent_grid(const void* kfn, size_t smem, int sm_count, uint64_t 
 template <int R, int MODE>
 static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   constexpr int TP = (R == 12 && MODE == MODE_COUNT) ? kTilePtsPos : kTilePts;
-  constexpr int STAGES = MODE == MODE_GRID ? 2 : (TP == kTilePtsPos ? 5 : ScanStages<R>::value);
+  constexpr int STAGES = MODE == MODE_GRID ? 2 : (TP == kTilePtsPos ? 5 : ScanStages<R>::value);  // (MODE_GRIDQ streams like a count)
   constexpr size_t smem = (size_t)STAGES * TP * R;
   static bool configured = false;
   auto kfn = k_scan_staged<R, MODE, STAGES, TP>;
@@ -1803,7 +1943,7 @@ template <int MODE>
 static int launch_direct_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   auto kfn = k_scan_direct<MODE>;
   unsigned grid = 0;
-  if (persistent_grid((const void*)kfn, 0, sm_count, p.n_tiles, MODE == MODE_GRID ? (int)kGridCtasPerSm : 8, &grid) != 0) return -1;
+  if (persistent_grid((const void*)kfn, 0, sm_count, p.n_tiles, (MODE == MODE_GRID || MODE == MODE_GRIDQ) ? (int)kGridCtasPerSm : 8, &grid) != 0) return -1;
   if (grid == 0) return 0;
   kfn<<<grid, kBlock, 0, st>>>(p);
   return check_launch();
@@ -1891,11 +2031,13 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
   if (variant == 2 && staged_supports(uniform_record_len)) {
     int rc = 1;
     if (mode == MODE_COUNT) rc = launch_staged_r<MODE_COUNT>(p, uniform_record_len, sm_count, st);
-    if (mode == MODE_GRID) rc = launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
+    if (mode == MODE_GRID)
+      rc = p.grid_sparse ? launch_staged_r<MODE_GRIDQ>(p, uniform_record_len, sm_count, st)
+                         : launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
     if (rc <= 0) return rc;
   }
   if (mode == MODE_COUNT) return launch_direct_t<MODE_COUNT>(p, sm_count, st);
-  return launch_direct_t<MODE_GRID>(p, sm_count, st);
+  return p.grid_sparse ? launch_direct_t<MODE_GRIDQ>(p, sm_count, st) : launch_direct_t<MODE_GRID>(p, sm_count, st);
 }
 
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream) {

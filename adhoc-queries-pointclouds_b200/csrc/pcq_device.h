@@ -15,7 +15,8 @@ constexpr int kTilePts = 512;  // records per tile
 constexpr int kBlock = 256;    // threads per CTA of the scan kernels
 constexpr int kPPT = kTilePts / kBlock;
 
-enum Mode : int { MODE_COUNT = 0, MODE_SELECT = 1, MODE_GRID = 2 };
+// MODE_GRIDQ: MODE_GRID for sparse matches — matching points go through a CTA match queue (kernels.cu)
+enum Mode : int { MODE_COUNT = 0, MODE_SELECT = 1, MODE_GRID = 2, MODE_GRIDQ = 3 };
 
 // One point range of one file, as resident in HBM.
 struct alignas(16) Segment {
@@ -129,6 +130,7 @@ struct ScanParams {
   const LaneDev* lanes;
   unsigned long long* tile_state;  // MODE_SELECT: decoupled look-back descriptors (n_tiles, zeroed)
   unsigned long long* ticket;      // MODE_SELECT: tile ticket counter (zeroed)
+  uint32_t grid_sparse;            // MODE_GRID: 1 = few points are expected to match: use the match-queue kernels
   uint32_t sel_bytes;              // MODE_SELECT: 1 = k_select_bytes (LAST class query, 32768-point units)
   uint32_t sel_ring;               // MODE_SELECT: record length when the launch qualifies for k_select_ring, else 0
   uint32_t debug;                  // measurement hooks, only in -DPCQ_DEBUG_HOOKS builds: 1 = skip the look-back, 2 = skip the emit
