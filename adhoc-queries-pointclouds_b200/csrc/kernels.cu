@@ -420,8 +420,8 @@ struct alignas(16) GridQEntry {
 // Where the kPPT points of a lane come from: straight from the tile ...
 template <class Src>
 struct TileFetch {
-  const Src& src;
-  const Hit (&h)[kPPT];
+  Src src;
+  Hit h[kPPT];  // (by value: a reference would force the array into local memory)
   uint64_t p0;
   __device__ __forceinline__ void xyz(int j, int32_t& x, int32_t& y, int32_t& z) const {
     x = h[j].x;
@@ -615,7 +615,10 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const Segment&
       ch.c = CandChunk();
       ch.lane = S.lane;
     }
-    grid_insert_tile(g, S, m, TileFetch<Src>{src, h, p0}, ch.c);
+    TileFetch<Src> f{src, {}, p0};
+#pragma unroll
+    for (int j = 0; j < kPPT; ++j) f.h[j] = h[j];
+    grid_insert_tile(g, S, m, f, ch.c);
   } else {
 #pragma unroll
     for (int j = 0; j < kPPT; ++j) {
