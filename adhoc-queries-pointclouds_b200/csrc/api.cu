@@ -72,6 +72,10 @@ struct pcq_ctx {
   // MODE_SELECT scratch
   unsigned long long* tile_state = nullptr;  // [0] = ticket, [1..] = descriptors
   uint64_t tile_state_cap = 0;
+  // scalar blocks of many collectors travel in one copy
+  void* d_gather = nullptr;
+  void* h_gather = nullptr;
+  size_t gather_cap = 0;
   // GRID export scratch (one export at a time)
   unsigned long long* part_scratch = nullptr;  // 2 * n_parts counters
   uint32_t part_scratch_cap = 0;
@@ -172,6 +176,34 @@ int upload(pcq_ctx* ctx, const void* src, size_t bytes, void** dev_out) {
 int read_devblock(pcq_collector* c, DevBlock* out) {
   CU(cudaMemcpyAsync(out, c->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, c->ctx->stream));
   CU(cudaStreamSynchronize(c->ctx->stream));
+  return PCQ_OK;
+}
+
+// the scalar blocks of all collectors of a launch: one gather kernel + one copy when there are many lanes
+int read_devblocks(pcq_ctx* ctx, pcq_collector* const* collectors, uint32_t n, const LaneDev* d_lanes, std::vector<DevBlock>& out) {
+  out.resize(n);
+  if (n <= 4 || d_lanes == nullptr) {
+    for (uint32_t l = 0; l < n; ++l)
+      CU(cudaMemcpyAsync(&out[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PCQ_OK;
+  }
+  const size_t bytes = (size_t)n * sizeof(DevBlock);
+  if (ctx->gather_cap < bytes) {
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    ctx->d_gather = ctx->h_gather = nullptr;
+    ctx->gather_cap = 0;
+    const size_t cap = round_up(bytes, 4096);
+    CU(cudaMalloc(&ctx->d_gather, cap));
+    CU(cudaMallocHost(&ctx->h_gather, cap));
+    ctx->gather_cap = cap;
+  }
+  if (launch_gather_blocks(d_lanes, n, (uint32_t)sizeof(DevBlock), ctx->d_gather, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_gather_blocks launch failed");
+  CU(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out.data(), ctx->h_gather, bytes);
   return PCQ_OK;
 }
 
@@ -771,10 +803,8 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
 
     bool retry = false;
     if (kind == PCQ_COLLECT_BUFFER) {
-      std::vector<DevBlock> blocks(n_collectors);
-      for (uint32_t l = 0; l < n_collectors; ++l)
-        CU(cudaMemcpyAsync(&blocks[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
+      std::vector<DevBlock> blocks;
+      RC(read_devblocks(ctx, collectors, n_collectors, static_cast<const LaneDev*>(d_lanes), blocks));
       for (uint32_t l = 0; l < n_collectors; ++l)
         if (blocks[l].count > collectors[l]->out_cap) retry = true;
       if (!retry) {
@@ -793,10 +823,8 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     }
 
     // GRID
-    std::vector<DevBlock> blocks(n_collectors);
-    for (uint32_t l = 0; l < n_collectors; ++l)
-      CU(cudaMemcpyAsync(&blocks[l], collectors[l]->dev, sizeof(DevBlock), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<DevBlock> blocks;
+    RC(read_devblocks(ctx, collectors, n_collectors, static_cast<const LaneDev*>(d_lanes), blocks));
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       const DevBlock& b = blocks[l];
@@ -899,6 +927,8 @@ static void ctx_free(pcq_ctx* ctx) {
   }
   if (ctx->tile_state) cudaFree(ctx->tile_state);
   if (ctx->part_scratch) cudaFree(ctx->part_scratch);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
   for (int i = 0; i < kChunkBuffers; ++i) {
     if (ctx->chunk[i]) cudaFree(ctx->chunk[i]);
     if (ctx->chunk_copied[i]) cudaEventDestroy(ctx->chunk_copied[i]);

@@ -2079,6 +2079,18 @@ int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, u
   return check_launch();
 }
 
+// one D2H copy instead of one per lane: the per-collector scalar blocks (first `block_bytes` bytes at lanes[l].count)
+__global__ void k_gather_blocks(const LaneDev* lanes, uint32_t n, uint32_t words, uint32_t* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * words; i += gridDim.x * blockDim.x)
+    out[i] = reinterpret_cast<const uint32_t*>(lanes[i / words].count)[i % words];
+}
+int launch_gather_blocks(const LaneDev* lanes, uint32_t n, uint32_t block_bytes, void* out, void* stream) {
+  if (n == 0) return 0;
+  const uint32_t words = block_bytes / 4u;
+  k_gather_blocks<<<(n * words + 255u) / 256u, 256, 0, (cudaStream_t)stream>>>(lanes, n, words, static_cast<uint32_t*>(out));
+  return check_launch();
+}
+
 int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream) {
   if (n == 0) return 0;
   k_grid_import<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, in, n);

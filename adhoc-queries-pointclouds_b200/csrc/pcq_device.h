@@ -152,6 +152,7 @@ int launch_grid_final_phase(const GridDev& g, uint64_t n, int phase, int sm_coun
 int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
                      unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points, unsigned long long* out_count,
                      int sm_count, void* stream);
+int launch_gather_blocks(const LaneDev* lanes, uint32_t n, uint32_t block_bytes, void* out, void* stream);
 int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream);
 
 // alias replay (alias.cu).  All asynchronous on `stream` unless stated otherwise.
