@@ -148,7 +148,9 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
 /* Wraps point data that is already resident in HBM.  For LAS `dev_point_data` points at record 0;
  * for LAST it points at the start of the transposed record block (column of the field at record
  * offset k starts at dev_point_data + k * desc->n_points, last_reader.rs:88-144).  The memory stays
- * owned by the caller.  `first_point_index` is the scan index of record 0 inside its file. */
+ * owned by the caller and must come from an allocator with at least 16-byte granularity (cudaMalloc, a framework's
+ * caching allocator, ...): record tiles move with 16-byte bulk copies, so up to 15 bytes past the last record may be
+ * read.  `first_point_index` is the scan index of record 0 inside its file. */
 int pcq_file_wrap_device(pcq_ctx* ctx, const pcq_file_desc* desc, const void* dev_point_data,
                          uint64_t first_point_index, pcq_file** out);
 
