@@ -719,11 +719,17 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
   }
   if (n_tiles == 0) return PCQ_OK;
 
+  // first-attempt capacities are guesses (an overflowing launch is re-run with the exact size); on multi-billion-point
+  // inputs they must not eat the HBM the exact size may need later: at most a sixth of what is free, shared by the lanes
+  size_t free_b = 0, total_b = 0;
+  if (kind != PCQ_COLLECT_COUNT) cudaMemGetInfo(&free_b, &total_b);
+  const uint64_t budget = std::max<uint64_t>((uint64_t)free_b / 6 / std::max<uint32_t>(n_collectors, 1u), 64u << 20);
   if (kind == PCQ_COLLECT_BUFFER) {
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       if (lane_points[l] == 0) continue;
-      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 20) + lane_points[l] / 8);
+      uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 20) + lane_points[l] / 8);
+      guess = std::min<uint64_t>(guess, std::max<uint64_t>(budget / 31, 1u << 20));
       RC(grow_out(c, c->out_len + guess));
     }
   } else if (kind == PCQ_COLLECT_GRID) {
@@ -732,7 +738,8 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
       if (lane_points[l] == 0) continue;
       RC(grid_restore(c));
       const uint64_t slack = (uint64_t)ctx->sm_count * kGridCtasPerSm * (kBlock / 32) * kCandChunk;
-      const uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16) + slack;
+      uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16);
+      guess = std::min<uint64_t>(guess, std::max<uint64_t>(budget / sizeof(Candidate), 1u << 22)) + slack;
       // Candidates are only ever dropped BETWEEN launches: what survives is every cell's current winner, which is
       // exactly what a later launch needs if one of its points makes the cell's key an aliased one (alias.cu).
       if (c->cand_len + guess > c->grid.cand_cap && c->cand_len > (1u << 20)) RC(prune_cands(c));

@@ -629,6 +629,24 @@ def test_large_device_resident_properties(pcq, ctx):
     assert len(np.unique(cell, axis=0)) == len(gp)
 
 
+def test_more_than_2_32_points_in_one_file(pcq):
+    """maximum sizes: one resident file of 4.5 G points (90 GB, more than a u32 can index), checked through
+    size-independent properties (tools/big_check.py) in its own process"""
+    import subprocess
+    import sys
+
+    import torch
+
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 120 * (1 << 30):
+        pytest.skip("needs 120 GB of free HBM")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "big_check.py"), "--points", "4500000000", "--layout", "las"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
+
+
 def test_density_exchange_over_nccl_when_two_gpus(pcq):
     """Real multi-rank run (one process per GPU, NCCL all-to-all) — needs >= 2 GPUs on the box."""
     import subprocess
