@@ -61,6 +61,31 @@ def plan_files(n_files: int, world: int) -> List[List[int]]:
     return [list(range(n_files * r // world, n_files * (r + 1) // world)) for r in range(world)]
 
 
+def gather_selected(ranges: Sequence[PointRange], selected: Sequence[np.ndarray], n_files: int, per_file: bool, group=None):
+    """Select (BufferCollector) over sharded point ranges: every rank passes its ranges and the scan-ordered records
+    its GPU selected from each; the per-range streams are concatenated on the host in (file, first point) order, which
+    is exactly the order one BufferCollector would have seen them in.  No data-path collective — only this gather.
+
+    per_file=False -> one array (run_search_sequential: one collector over all files, main.rs:122-144)
+    per_file=True  -> one array per file (run_search_parallel: one collector per file, main.rs:146-183)."""
+    import torch.distributed as dist
+
+    mine = [(r.file, r.first_point, np.ascontiguousarray(p).tobytes()) for r, p in zip(ranges, selected)]
+    world = dist.get_world_size(group)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    pieces = sorted((item for part in gathered for item in part), key=lambda t: (t[0], t[1]))
+    from .binding import POINT_DTYPE
+
+    def cat(items):
+        raw = b"".join(b for _, _, b in items)
+        return np.frombuffer(raw, dtype=POINT_DTYPE).copy()
+
+    if not per_file:
+        return cat(pieces)
+    return [cat([it for it in pieces if it[0] == f]) for f in range(n_files)]
+
+
 def mix64(x: np.ndarray) -> np.ndarray:
     """The owner hash of kernels.cu (murmur3 finaliser) on uint64 arrays."""
     x = x.astype(np.uint64).copy()

@@ -2,7 +2,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_density_nccl.py
 One navvis-shape file is cut into tile-aligned point ranges (one per rank); every rank scans its range into a
 local cell table, the per-cell candidates travel by owner with one all-to-all, owners merge, rank 0 checks the
-union against the oracle's single sequential fold.  Also checks the sharded count."""
+union against the oracle's single sequential fold.  Also checks the sharded count and the sharded select (per-range
+record streams concatenated in range order == one BufferCollector over the whole file)."""
 import os
 import sys
 from pathlib import Path
@@ -43,6 +44,14 @@ def main():
                 searcher.search_files(dfs, impl, [cc])
             t = torch.tensor([cc.point_count()], dtype=torch.int64, device=f"cuda:{local}")
             dist.all_reduce(t)
+            # select: every rank compacts its ranges in scan order, the host concatenates them in range order
+            sel = []
+            for df in dfs:
+                bc = pcq.BufferCollector(ctx)
+                searcher.search_files([df], impl, [bc])
+                p = bc.points()
+                sel.append(p if p is not None else np.zeros(0, pcq.POINT_DTYPE))
+            selected = sh.gather_selected(ranges, sel, 1, per_file=False)
             # density: local table -> candidates by owner -> all-to-all -> merge
             lg = pcq.GridSampledCollector(qmin, qmax, S.NAVVIS_DENSITY, ctx=ctx)
             if dfs:
@@ -57,7 +66,10 @@ def main():
                 orc.search_file(img, "las", og, bounds=(qmin, qmax))
                 oc = orc.Collector(orc.COLLECT_COUNT)
                 orc.search_file(img, "las", oc, bounds=(qmin, qmax))
-                good = same_point_set(got, og.points()) and int(t.item()) == oc.point_count()
+                ob = orc.Collector(orc.COLLECT_BUFFER)
+                orc.search_file(img, "las", ob, bounds=(qmin, qmax))
+                good = (same_point_set(got, og.points()) and int(t.item()) == oc.point_count()
+                        and selected.tobytes() == ob.points().tobytes())
                 print(f"world={world} fma={fma} box={qmax}: count {int(t.item())} cells {len(got)} -> {'OK' if good else 'MISMATCH'}", flush=True)
                 ok = ok and good
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")

@@ -141,10 +141,27 @@ def _worker(rank, world, port, tmpdir):
     mine = np.array([p for _, p in merged.values()], dtype=pcq.POINT_DTYPE) if merged else np.zeros(0, pcq.POINT_DTYPE)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine.tobytes())
+    # ---- select: point-range sharding, per-range record streams concatenated in scan order (no collective) ----
+    sel = []
+    for r in plan:
+        xyz, cls = arrays[r.file]
+        full = make_file(xyz, cls, fmt=2, scale=scale, offset=offset, seed=r.file)
+        h = npo.parse_header(full)
+        R, off = h["record_len"], h["off"]
+        img = np.concatenate([full[:off], full[off + r.first_point * R: off + (r.first_point + r.n_points) * R]]).copy()
+        img[107:111] = np.frombuffer(np.uint32(r.n_points).tobytes(), np.uint8)
+        c = orc.Collector(orc.COLLECT_BUFFER)
+        orc.search_file(img, "las", c, bounds=(qmin, qmax))
+        sel.append(c.points())
+    seq = sh.gather_selected(plan, sel, len(sizes), per_file=False)
+    per = sh.gather_selected(plan, sel, len(sizes), per_file=True)
     if rank == 0:
         allp = np.frombuffer(b"".join(gathered), dtype=pcq.POINT_DTYPE)
         np.save(os.path.join(tmpdir, "density.npy"), allp.view(np.uint8))
         np.save(os.path.join(tmpdir, "count.npy"), np.array([total_count]))
+        np.save(os.path.join(tmpdir, "select_seq.npy"), seq.view(np.uint8))
+        for f, a in enumerate(per):
+            np.save(os.path.join(tmpdir, f"select_{f}.npy"), a.view(np.uint8))
     dist.destroy_process_group()
 
 
@@ -161,11 +178,23 @@ def test_two_rank_count_and_density_exchange(pcq, tmp_path):
     qmin, qmax = (-20.0, -18.0, -9.0), (30.0, 33.0, 45.0)
     og = orc.Collector(orc.COLLECT_GRID, qmin, qmax, 3.7)
     oc = orc.Collector(orc.COLLECT_COUNT)
+    ob = orc.Collector(orc.COLLECT_BUFFER)
+    per_file = []
     for f, n in enumerate(sizes):
         xyz, cls = rng.integers(0, 60_000, size=(n, 3), dtype=np.int32), rng.integers(0, 5, size=n).astype(np.uint8)
         img = make_file(xyz, cls, fmt=2, scale=scale, offset=offset, seed=f)
         orc.search_file(img, "las", og, bounds=(qmin, qmax))
         orc.search_file(img, "las", oc, bounds=(qmin, qmax))
+        orc.search_file(img, "las", ob, bounds=(qmin, qmax))
+        one = orc.Collector(orc.COLLECT_BUFFER)
+        orc.search_file(img, "las", one, bounds=(qmin, qmax))
+        per_file.append(one.points())
+    # select over sharded point ranges == one BufferCollector over all files / one per file, byte for byte
+    from tests.helpers import same_point_seq
+
+    assert same_point_seq(np.load(tmp_path / "select_seq.npy").view(pcq.POINT_DTYPE), ob.points())
+    for f, want in enumerate(per_file):
+        assert same_point_seq(np.load(tmp_path / f"select_{f}.npy").view(pcq.POINT_DTYPE), want)
     got = np.load(tmp_path / "density.npy").view(pcq.POINT_DTYPE)
     assert int(np.load(tmp_path / "count.npy")[0]) == oc.point_count() > 1000
     assert og.point_count() > 300
