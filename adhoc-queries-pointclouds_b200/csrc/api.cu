@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -85,6 +86,11 @@ struct pcq_ctx {
   size_t chunk_cap = 0;
   cudaEvent_t chunk_copied[kChunkBuffers] = {nullptr, nullptr, nullptr};
   cudaEvent_t chunk_free[kChunkBuffers] = {nullptr, nullptr, nullptr};
+  // pinned bounce ring for file images in pageable memory (mmap'ed files): host threads copy a piece in, the copy
+  // engine takes it from there at link speed
+  void* bounce[kChunkBuffers] = {nullptr, nullptr, nullptr};
+  size_t bounce_cap = 0;
+  cudaEvent_t bounce_done[kChunkBuffers] = {nullptr, nullptr, nullptr};
 };
 
 struct pcq_file {
@@ -205,6 +211,35 @@ int read_devblocks(pcq_ctx* ctx, pcq_collector* const* collectors, uint32_t n, c
   CU(cudaStreamSynchronize(ctx->stream));
   std::memcpy(out.data(), ctx->h_gather, bytes);
   return PCQ_OK;
+}
+
+// host-side copy of a piece into the pinned bounce ring, split over a few threads (one thread moves ~10 GB/s)
+void parallel_memcpy(void* dst, const void* src, size_t n) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t threads = std::min<size_t>({8, hw ? hw / 2 : 2, n / (8u << 20) + 1});
+  if (threads <= 1) {
+    std::memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = round_up((n + threads - 1) / threads, 4096);
+  for (size_t t = 1; t < threads; ++t) {
+    const size_t a = t * per;
+    if (a >= n) break;
+    const size_t len = std::min(per, n - a);
+    pool.emplace_back([=] { std::memcpy(static_cast<uint8_t*>(dst) + a, static_cast<const uint8_t*>(src) + a, len); });
+  }
+  std::memcpy(dst, src, std::min(per, n));
+  for (std::thread& t : pool) t.join();
+}
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
 int layout_of_ext(const char* ext) {
@@ -940,6 +975,8 @@ static void ctx_free(pcq_ctx* ctx) {
     if (ctx->chunk[i]) cudaFree(ctx->chunk[i]);
     if (ctx->chunk_copied[i]) cudaEventDestroy(ctx->chunk_copied[i]);
     if (ctx->chunk_free[i]) cudaEventDestroy(ctx->chunk_free[i]);
+    if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+    if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1369,6 +1406,33 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     if (!ctx->chunk_copied[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_copied[b], cudaEventDisableTiming));
     if (!ctx->chunk_free[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_free[b], cudaEventDisableTiming));
   }
+  // file images in pageable memory (a memory-mapped file, las.rs:24-31) go through a pinned bounce ring
+  std::vector<char> pageable(n_files, 0);
+  bool any_pageable = false;
+  for (uint32_t i = 0; i < n_files; ++i) {
+    pageable[i] = is_pinned_host(file_bytes[i]) ? 0 : 1;
+    any_pageable |= pageable[i] != 0;
+  }
+  if (std::getenv("PCQ_NO_BOUNCE")) any_pageable = false, std::fill(pageable.begin(), pageable.end(), 0);
+  if (any_pageable) {
+    const size_t want = std::max(ctx->chunk_cap, chunk_bytes) + 1024;
+    if (ctx->bounce_cap < want) {
+      CU(cudaStreamSynchronize(ctx->copy_stream));
+      for (int b = 0; b < kChunkBuffers; ++b) {
+        if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
+        ctx->bounce[b] = nullptr;
+      }
+      ctx->bounce_cap = 0;
+      for (int b = 0; b < kChunkBuffers; ++b)
+        if (cudaMallocHost(&ctx->bounce[b], want) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes of host memory for the staging ring", want);
+        }
+      ctx->bounce_cap = want;
+    }
+    for (int b = 0; b < kChunkBuffers; ++b)
+      if (!ctx->bounce_done[b]) CU(cudaEventCreateWithFlags(&ctx->bounce_done[b], cudaEventDisableTiming));
+  }
 
   struct Piece {
     uint32_t file;
@@ -1424,6 +1488,7 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     const uint8_t *rec, *cls, *rgb;
   };
   std::vector<Staged> staged(pieces.size());
+  bool bounce_used[kChunkBuffers] = {false, false, false};
   auto issue_copy = [&](size_t j) -> int {
     const Piece& pc = pieces[j];
     const FilePlan& fp = fps[pc.file];
@@ -1433,29 +1498,44 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     const uint8_t* src = static_cast<const uint8_t*>(file_bytes[pc.file]) + fp.d.point_data_off;
     const uint64_t N = fp.d.n_points;
     Staged st{nullptr, nullptr, nullptr};
+    const bool via_bounce = pageable[pc.file] != 0;
+    uint8_t* hb = via_bounce ? static_cast<uint8_t*>(ctx->bounce[b]) : nullptr;
+    if (via_bounce && bounce_used[b]) CU(cudaEventSynchronize(ctx->bounce_done[b]));  // the slot's last H2D has left it
+    // one column (or the record block): host bytes -> [pinned bounce slot ->] device chunk at offset o
+    auto put = [&](size_t o, const uint8_t* from, size_t n) -> int {
+      if (via_bounce) {
+        parallel_memcpy(hb + o, from, n);
+        CU(cudaMemcpyAsync(dst + o, hb + o, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      } else {
+        CU(cudaMemcpyAsync(dst + o, from, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
+      return PCQ_OK;
+    };
     if (fp.d.layout == PCQ_LAYOUT_LAS) {
-      CU(cudaMemcpyAsync(dst, src + pc.first * fp.d.record_len, pc.n * fp.d.record_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+      RC(put(0, src + pc.first * fp.d.record_len, pc.n * fp.d.record_len));
       st.rec = dst;
     } else {
       size_t o = 0;
       if (fp.need_pos) {
-        CU(cudaMemcpyAsync(dst + o, src + pc.first * 12, pc.n * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+        RC(put(o, src + pc.first * 12, pc.n * 12));
         st.rec = dst + o;
         o += round_up(pc.n * 12, 256);
       } else {
         st.rec = dst;  // never dereferenced by a class count
       }
       if (fp.need_cls) {
-        CU(cudaMemcpyAsync(dst + o, src + (uint64_t)cls_offset_in_record(fp.d.format) * N + pc.first, pc.n,
-                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        RC(put(o, src + (uint64_t)cls_offset_in_record(fp.d.format) * N + pc.first, pc.n));
         st.cls = dst + o;
         o += round_up(pc.n, 256);
       }
       if (fp.need_rgb) {
-        CU(cudaMemcpyAsync(dst + o, src + (uint64_t)rgb_offset_in_record(fp.d.format) * N + pc.first * 6, pc.n * 6,
-                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        RC(put(o, src + (uint64_t)rgb_offset_in_record(fp.d.format) * N + pc.first * 6, pc.n * 6));
         st.rgb = dst + o;
       }
+    }
+    if (via_bounce) {
+      CU(cudaEventRecord(ctx->bounce_done[b], ctx->copy_stream));
+      bounce_used[b] = true;
     }
     staged[j] = st;
     CU(cudaEventRecord(ctx->chunk_copied[b], ctx->copy_stream));

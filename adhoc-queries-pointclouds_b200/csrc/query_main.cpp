@@ -180,7 +180,17 @@ int main(int argc, char** argv) {
     if (!bounds && klass < 0)
       throw Error(PCQ_ERR_ARG, "Found neither BOUNDS nor CLASS argument but exactly one of these arguments is required!");
 
+    const bool timing = std::getenv("PCQ_CLI_TIMING") != nullptr;  // phase times on stderr (not part of the reference's output)
+    auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    const double t_args = since_start();
+    // The process uses ONE GPU: hiding the others before the first CUDA call keeps the driver from initialising every
+    // device of the box (seconds on an 8-GPU node; the reference's throughput line includes start-up, main.rs:192, 309-316)
+    if (std::getenv("CUDA_VISIBLE_DEVICES") == nullptr) {
+      setenv("CUDA_VISIBLE_DEVICES", std::to_string(gpu).c_str(), 1);
+      gpu = 0;
+    }
     Context ctx(gpu);
+    const double t_ctx = since_start();
     std::unique_ptr<Searcher> searcher;
     if (bounds) searcher.reset(new BoundsSearcher(ctx, *bounds));
     else searcher.reset(new ClassSearcher(ctx, (uint8_t)klass));
@@ -212,6 +222,9 @@ int main(int argc, char** argv) {
       run_search_sequential(input_files, *searcher, impl, *collector, *dumper);
     }
 
+    if (timing)
+      std::fprintf(stderr, "[pcq timing] listing + arguments %.3f s, device context %.3f s, search + output %.3f s\n", t_args,
+                   t_ctx - t_args, since_start() - t_ctx);
     const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     const double throughput_mibs = (double)total_file_size / elapsed / 1048576.0;
     std::printf("Searched %.2f MiB in %.2fs (throughput: %.2fMiB/s)\n", total_file_size_mib, elapsed, throughput_mibs);
