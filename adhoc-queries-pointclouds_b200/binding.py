@@ -85,6 +85,26 @@ class SynthSpec(C.Structure):
     ]
 
 
+INDEX_CHUNK_POINTS = 8192
+
+# pcq_chunk_header: integer AABB of the raw x/y/z fields + set of class bytes of one chunk (64 bytes)
+CHUNK_HEADER_DTYPE = np.dtype(
+    [("lo", "<i4", (3,)), ("hi", "<i4", (3,)), ("cls_bits", "<u4", (8,)), ("n_points", "<u4"), ("pad", "<u4")]
+)
+assert CHUNK_HEADER_DTYPE.itemsize == 64
+
+
+class ScanStats(C.Structure):
+    _fields_ = [
+        ("points_total", C.c_uint64),
+        ("points_scanned", C.c_uint64),
+        ("chunks_total", C.c_uint64),
+        ("chunks_skipped", C.c_uint64),
+        ("segments", C.c_uint32),
+        ("pad_", C.c_uint32),
+    ]
+
+
 class PcqError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"pcq error {code}: {message}")
@@ -128,6 +148,11 @@ def _load() -> C.CDLL:
         "pcq_search_files": (C.c_int, [vp, P(vp), u32, P(Query), P(vp), u32]),
         "pcq_search_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), P(vp), u32]),
         "pcq_search_host_files_multi": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), u32, P(vp), u32]),
+        "pcq_file_build_index": (C.c_int, [vp]),
+        "pcq_file_drop_index": (None, [vp]),
+        "pcq_file_index": (C.c_int, [vp, P(vp), P(u64)]),
+        "pcq_ctx_set_auto_index": (C.c_int, [vp, u32]),
+        "pcq_ctx_last_scan_stats": (C.c_int, [vp, P(ScanStats)]),
         "pcq_host_alloc": (C.c_int, [sz, P(vp)]),
         "pcq_host_free": (None, [vp]),
         "pcq_grid_export_candidates": (C.c_int, [vp, u32, P(vp), P(u64)]),

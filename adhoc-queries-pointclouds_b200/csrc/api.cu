@@ -91,6 +91,9 @@ struct pcq_ctx {
   void* bounce[kChunkBuffers] = {nullptr, nullptr, nullptr};
   size_t bounce_cap = 0;
   cudaEvent_t bounce_done[kChunkBuffers] = {nullptr, nullptr, nullptr};
+  // chunk index
+  uint32_t auto_index_after = 0;  // 0 = never build one unasked
+  pcq_scan_stats stats{};
 };
 
 struct pcq_file {
@@ -105,6 +108,9 @@ struct pcq_file {
   const uint8_t* rgb = nullptr;
   bool has_scan_base = false;
   uint64_t scan_base = 0;
+  // chunk index (index.cu): host copy of the headers (what the per-search filter walks), scans seen so far
+  std::vector<pcq_chunk_header> index;
+  uint32_t scans = 0;
 };
 
 struct pcq_collector {
@@ -712,6 +718,10 @@ double expected_match_fraction(const pcq_file_desc& d, const pcq_query* q) {
   return f;
 }
 
+// k_class_count_soa walks the segments one after the other with the whole grid: fine for files, not for the thousands
+// of chunk runs an indexed launch can hold (those take the tile-scheduled scan)
+constexpr size_t kSoaCountMaxSegs = 256;
+
 int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_collector* const* collectors,
               uint32_t n_collectors, const std::vector<uint64_t>& lane_points, double match_fraction = -1.0) {
   const int kind = collectors[0]->kind;
@@ -755,16 +765,25 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
   if (n_tiles == 0) return PCQ_OK;
 
   // first-attempt capacities are guesses (an overflowing launch is re-run with the exact size); on multi-billion-point
-  // inputs they must not eat the HBM the exact size may need later: at most a sixth of what is free, shared by the lanes
-  size_t free_b = 0, total_b = 0;
-  if (kind != PCQ_COLLECT_COUNT) cudaMemGetInfo(&free_b, &total_b);
-  const uint64_t budget = std::max<uint64_t>((uint64_t)free_b / 6 / std::max<uint32_t>(n_collectors, 1u), 64u << 20);
+  // inputs they must not eat the HBM the exact size may need later: at most a sixth of what is free, shared by the lanes.
+  // cudaMemGetInfo is only asked when some collector really has to grow: its cost is anything from microseconds to
+  // milliseconds, and a collector that is reused (reset, next query) already owns what it needs.
+  uint64_t budget = 0;
+  auto growth_budget = [&]() -> uint64_t {
+    if (budget == 0) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      budget = std::max<uint64_t>((uint64_t)free_b / 6 / std::max<uint32_t>(n_collectors, 1u), 64u << 20);
+    }
+    return budget;
+  };
   if (kind == PCQ_COLLECT_BUFFER) {
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       if (lane_points[l] == 0) continue;
       uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 20) + lane_points[l] / 8);
-      guess = std::min<uint64_t>(guess, std::max<uint64_t>(budget / 31, 1u << 20));
+      if (c->out_cap >= c->out_len + guess) continue;
+      guess = std::min<uint64_t>(guess, std::max<uint64_t>(growth_budget() / 31, 1u << 20));
       RC(grow_out(c, c->out_len + guess));
     }
   } else if (kind == PCQ_COLLECT_GRID) {
@@ -774,7 +793,9 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
       RC(grid_restore(c));
       const uint64_t slack = (uint64_t)ctx->sm_count * kGridCtasPerSm * (kBlock / 32) * kCandChunk;
       uint64_t guess = std::min<uint64_t>(lane_points[l], (1u << 22) + lane_points[l] / 16);
-      guess = std::min<uint64_t>(guess, std::max<uint64_t>(budget / sizeof(Candidate), 1u << 22)) + slack;
+      if (c->cand_len + guess + slack > c->grid.cand_cap)
+        guess = std::min<uint64_t>(guess, std::max<uint64_t>(growth_budget() / sizeof(Candidate), 1u << 22));
+      guess += slack;
       // Candidates are only ever dropped BETWEEN launches: what survives is every cell's current winner, which is
       // exactly what a later launch needs if one of its points makes the cell's key an aliased one (alias.cu).
       if (c->cand_len + guess > c->grid.cand_cap && c->cand_len > (1u << 20)) RC(prune_cands(c));
@@ -833,7 +854,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     }
 
     int lrc;
-    if (mode == MODE_COUNT && q->kind == PCQ_QUERY_CLASS && all_last) {
+    if (mode == MODE_COUNT && q->kind == PCQ_QUERY_CLASS && all_last && segs.size() <= kSoaCountMaxSegs) {
       lrc = launch_class_count_soa(P, ctx->sm_count, ctx->stream);
     } else {
       lrc = launch_scan(variant, mode, P, R, min_align, ctx->sm_count, ctx->stream);
@@ -1126,6 +1147,71 @@ void pcq_file_release(pcq_file* f) {
   delete f;
 }
 
+// ---- chunk index ---------------------------------------------------------------------------------
+
+int pcq_file_build_index(pcq_file* f) {
+  if (!f) return fail(PCQ_ERR_ARG, "null file");
+  if (!f->index.empty() || f->n_points == 0) return PCQ_OK;
+  pcq_ctx* ctx = f->ctx;
+  RC(use_device(ctx));
+  ChunkIndexArgs a{};
+  a.rec = f->rec;
+  a.cls = f->cls;
+  a.n_points = f->n_points;
+  a.n_chunks = (f->n_points + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS;
+  a.layout = f->desc.layout;
+  a.record_len = f->desc.layout == PCQ_LAYOUT_LAS ? f->desc.record_len : 12u;
+  a.cls_off = cls_offset_in_record(f->desc.format);
+  a.align = field_alignment(f->rec, a.record_len);
+  void* d_headers = nullptr;
+  const size_t bytes = (size_t)a.n_chunks * sizeof(pcq_chunk_header);
+  if (cudaMalloc(&d_headers, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM for chunk headers", bytes);
+  }
+  std::vector<pcq_chunk_header> headers;
+  int rc = PCQ_OK;
+  try {
+    headers.resize(a.n_chunks);
+  } catch (const std::bad_alloc&) {
+    rc = fail(PCQ_ERR_NOMEM, "out of host memory for %llu chunk headers", (unsigned long long)a.n_chunks);
+  }
+  if (rc == PCQ_OK && launch_chunk_index(a, static_cast<pcq_chunk_header*>(d_headers), ctx->sm_count, ctx->stream) != 0)
+    rc = fail(PCQ_ERR_CUDA, "chunk index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == PCQ_OK) {
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(headers.data(), d_headers, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(PCQ_ERR_CUDA, "chunk index: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_headers);
+  if (rc == PCQ_OK) f->index.swap(headers);
+  return rc;
+}
+
+void pcq_file_drop_index(pcq_file* f) {
+  if (f) std::vector<pcq_chunk_header>().swap(f->index);
+}
+
+int pcq_file_index(const pcq_file* f, const pcq_chunk_header** out_headers, uint64_t* out_n) {
+  if (!f || !out_headers || !out_n) return fail(PCQ_ERR_ARG, "null argument");
+  *out_headers = f->index.empty() ? nullptr : f->index.data();
+  *out_n = f->index.size();
+  return PCQ_OK;
+}
+
+int pcq_ctx_set_auto_index(pcq_ctx* ctx, uint32_t after_n_scans) {
+  if (!ctx) return fail(PCQ_ERR_ARG, "null context");
+  ctx->auto_index_after = after_n_scans;
+  return PCQ_OK;
+}
+
+int pcq_ctx_last_scan_stats(const pcq_ctx* ctx, pcq_scan_stats* out) {
+  if (!ctx || !out) return fail(PCQ_ERR_ARG, "null argument");
+  *out = ctx->stats;
+  return PCQ_OK;
+}
+
 // ---- collectors ----------------------------------------------------------------------------------
 
 int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const double gmax[3], double cell_size,
@@ -1302,6 +1388,44 @@ int pcq_collector_points(pcq_collector* c, const pcq_point** out_points, uint64_
 
 // ---- the scan ------------------------------------------------------------------------------------
 
+namespace {
+
+bool chunk_may_match(const pcq_chunk_header& h, const pcq_query* q, const SegmentPlan& plan) {
+  if (q->kind == PCQ_QUERY_BOUNDS) {
+    // a record matches iff lo <= v <= hi on every axis (las.rs:106-119): the chunk's extent must overlap that box
+    for (int a = 0; a < 3; ++a)
+      if (h.hi[a] < plan.lo[a] || h.lo[a] > plan.hi[a]) return false;
+    return true;
+  }
+  return ((h.cls_bits[q->cls >> 5] >> (q->cls & 31u)) & 1u) != 0;
+}
+
+struct ChunkRun {
+  uint64_t first, end;  // chunks [first, end)
+};
+
+// Runs of chunks of an indexed file that can hold a match.  Runs less than `gap` chunks apart are joined (scanning a
+// few chunks that cannot match is cheaper than another point range in the launch); returns the chunks that may match.
+uint64_t surviving_runs(const pcq_file* f, const pcq_query* q, const SegmentPlan& plan, uint64_t gap, std::vector<ChunkRun>& runs) {
+  runs.clear();
+  uint64_t may = 0;
+  const uint64_t n = f->index.size();
+  for (uint64_t c = 0; c < n; ++c) {
+    if (!chunk_may_match(f->index[c], q, plan)) continue;
+    ++may;
+    if (!runs.empty() && c - runs.back().end < gap)
+      runs.back().end = c + 1;
+    else
+      runs.push_back({c, c + 1});
+  }
+  return may;
+}
+
+constexpr uint64_t kIndexJoinGap = 4;        // chunks
+constexpr size_t kIndexMaxRunsPerFile = 4096;
+
+}  // namespace
+
 static int check_search_args(pcq_ctx* ctx, uint32_t n_files, const pcq_query* q, pcq_collector* const* collectors,
                              uint32_t n_collectors) {
   if (!ctx || !q || !collectors) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
@@ -1330,6 +1454,8 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
   std::vector<uint64_t> lane_points(n_collectors, 0);
   bool frac_known = true;
   double frac_pts = 0.0, all_pts = 0.0;
+  pcq_scan_stats st{};
+  std::vector<ChunkRun> runs;
   for (uint32_t i = 0; i < n_files; ++i) {
     pcq_file* f = files[i];
     if (!f) return fail(PCQ_ERR_ARG, "null file %u", i);
@@ -1341,17 +1467,58 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     SegmentPlan plan;
     RC(plan_file(f->desc, f->raw_format, query, &plan));
     if (plan.skip || f->n_points == 0) continue;
-    Segment s;
-    fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base, query->kind);
-    lane_points[lane] += f->n_points;
-    segs.push_back(s);
+    if (ctx->auto_index_after != 0 && f->index.empty() && f->scans >= ctx->auto_index_after) RC(pcq_file_build_index(f));
+    f->scans++;
+    st.points_total += f->n_points;
+
+    // chunk index: launch over the runs of chunks that can hold a match.  Every run keeps its place in the scan
+    // order (scan_base) and on its lane, so counts, record streams and density ties are those of the full scan.
+    bool whole = true;
+    if (!f->index.empty()) {
+      const uint64_t n_chunks = f->index.size();
+      uint64_t gap = kIndexJoinGap;
+      const uint64_t may = surviving_runs(f, query, plan, gap, runs);
+      while (runs.size() > kIndexMaxRunsPerFile) surviving_runs(f, query, plan, gap *= 4, runs);
+      uint64_t kept = 0;
+      for (const ChunkRun& r : runs) kept += r.end - r.first;
+      st.chunks_total += n_chunks;
+      if (may == 0) {
+        st.chunks_skipped += n_chunks;
+        continue;
+      }
+      if (kept * 10 < n_chunks * 9) {  // below that a fragmented launch saves too little
+        whole = false;
+        st.chunks_skipped += n_chunks - kept;
+        const uint64_t R = f->desc.layout == PCQ_LAYOUT_LAS ? f->desc.record_len : 12u;
+        for (const ChunkRun& r : runs) {
+          const uint64_t p0 = r.first * PCQ_INDEX_CHUNK_POINTS;
+          const uint64_t n = std::min<uint64_t>(r.end * PCQ_INDEX_CHUNK_POINTS, f->n_points) - p0;
+          Segment s;
+          fill_segment(&s, f->desc, f->rec + p0 * R, f->cls ? f->cls + p0 : nullptr, f->rgb ? f->rgb + p0 * 6 : nullptr, n, plan,
+                       lane, base + p0, query->kind);
+          lane_points[lane] += n;
+          all_pts += (double)n;
+          segs.push_back(s);
+        }
+      }
+    }
+    // the matches the header box promises are all in the ranges that are left
     const double fr = expected_match_fraction(f->desc, query);
     if (fr < 0.0) frac_known = false;
     frac_pts += (fr < 0.0 ? 0.0 : fr) * (double)f->n_points;
-    all_pts += (double)f->n_points;
+    if (whole) {
+      Segment s;
+      fill_segment(&s, f->desc, f->rec, f->cls, f->rgb, f->n_points, plan, lane, base, query->kind);
+      lane_points[lane] += f->n_points;
+      all_pts += (double)f->n_points;
+      segs.push_back(s);
+    }
   }
+  st.points_scanned = (uint64_t)all_pts;
+  st.segments = (uint32_t)segs.size();
+  ctx->stats = st;
   return run_batch(ctx, segs, query, collectors, n_collectors, lane_points,
-                   frac_known && all_pts > 0.0 ? frac_pts / all_pts : -1.0);
+                   frac_known && all_pts > 0.0 ? std::min(1.0, frac_pts / all_pts) : -1.0);
 }
 
 int pcq_host_alloc(size_t n_bytes, void** out) {

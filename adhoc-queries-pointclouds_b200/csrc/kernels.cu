@@ -559,6 +559,26 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
   }
 }
 
+// Index of the segment that holds `tile`, searching forward from `cur` (segments are ordered by first_tile).  A launch
+// over the surviving chunk runs of an index (api.cu) can hold thousands of short segments, and a CTA's next tile lies
+// gridDim tiles further on: gallop, then bisect, instead of walking.
+__device__ __forceinline__ uint32_t seg_forward(const ScanParams& P, uint32_t cur, uint64_t tile) {
+  if (cur + 1 < P.n_segs && tile >= P.segs[cur + 1].first_tile) {
+    uint32_t lo = cur + 1, step = 1;
+    while (lo + step < P.n_segs && tile >= P.segs[lo + step].first_tile) {
+      lo += step;
+      step <<= 1;
+    }
+    uint32_t hi = lo + step < P.n_segs ? lo + step : P.n_segs;  // segs[lo].first_tile <= tile < segs[hi].first_tile
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (tile >= P.segs[mid].first_tile) lo = mid; else hi = mid;
+    }
+    cur = lo;
+  }
+  return cur;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-tile work shared by the direct and the staged scan kernels (MODE_COUNT / MODE_GRID)
 // ------------------------------------------------------------------------------------------------
@@ -693,7 +713,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_direct(ScanParams P) {
   for (uint64_t iter = 0;; ++iter) {
     const uint64_t tile = (uint64_t)blockIdx.x + iter * (uint64_t)gridDim.x;
     if (tile >= P.n_tiles) break;
-    while (seg_cursor + 1 < P.n_segs && tile >= P.segs[seg_cursor + 1].first_tile) ++seg_cursor;
+    seg_cursor = seg_forward(P, seg_cursor, tile);
     if (seg_cursor != seg_i) {
       // segment change: flush the per-lane match count, cache the new segment in shared memory
       if constexpr (MODE == MODE_COUNT) {
@@ -807,7 +827,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
       stage_tile[s] = ~0ull;
       return;
     }
-    while (prod_seg + 1 < P.n_segs && tile >= P.segs[prod_seg + 1].first_tile) ++prod_seg;
+    prod_seg = seg_forward(P, prod_seg, tile);
     const Segment* sg = P.segs + prod_seg;
     const uint64_t p0 = (tile - sg->first_tile) * (uint64_t)TP;
     const uint64_t rem = sg->n_points - p0;
@@ -1185,7 +1205,7 @@ __device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelU
       if (++end_marks == (uint32_t)kSelLbWarps) break;
       continue;
     }
-    while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
+    seg_cur = seg_forward(P, seg_cur, tile);
     const Segment* sg = P.segs + seg_cur;
     const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
     uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
@@ -1460,7 +1480,7 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
         }
         break;
       }
-      while (seg_cur + 1 < P.n_segs && tile >= P.segs[seg_cur + 1].first_tile) ++seg_cur;
+      seg_cur = seg_forward(P, seg_cur, tile);
       const Segment* sg = P.segs + seg_cur;
       const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
       uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);

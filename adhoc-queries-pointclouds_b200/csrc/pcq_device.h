@@ -163,4 +163,17 @@ int alias_prewinners(const GridDev& g, uint64_t n_cands, const unsigned long lon
 // synchronises the stream (temporary storage is freed before returning)
 int alias_replay(const GridDev& g, uint64_t n, AliasState* d_states, int sm_count, void* stream);
 
+// chunk index build (index.cu): one pcq_chunk_header per PCQ_INDEX_CHUNK_POINTS points of a resident file range
+struct ChunkIndexArgs {
+  const uint8_t* rec;   // LAS: record 0.  LAST: positions column
+  const uint8_t* cls;   // LAST: class column (LAS: unused)
+  uint64_t n_points;
+  uint64_t n_chunks;
+  uint32_t record_len;  // LAS only
+  uint32_t cls_off;     // LAS only: the byte the class search compares (15 / 16)
+  uint8_t layout;
+  uint8_t align;        // alignment of the x/y/z fields: 4, 2 or 1
+};
+int launch_chunk_index(const ChunkIndexArgs& a, pcq_chunk_header* out, int sm_count, void* stream);
+
 }  // namespace pcq

@@ -57,6 +57,16 @@ class Context:
     def launch_count(self) -> int:
         return int(lib.pcq_ctx_launch_count(self.handle))
 
+    def set_auto_index(self, after_n_scans: int):
+        """Build a resident file's chunk index when it is scanned for the (n+1)-th time (0 = never)."""
+        check(lib.pcq_ctx_set_auto_index(self.handle, int(after_n_scans)))
+
+    @property
+    def last_scan_stats(self) -> B.ScanStats:
+        st = B.ScanStats()
+        check(lib.pcq_ctx_last_scan_stats(self.handle, C.byref(st)))
+        return st
+
 
 _default_ctx: Optional[Context] = None
 
@@ -103,6 +113,23 @@ class DeviceFile:
         d = B.FileDesc()
         check(lib.pcq_file_desc_get(self.handle, C.byref(d)))
         return d
+
+    def build_index(self):
+        """Chunk headers (improvements.md:3-10): later searches launch over the chunks that can hold a match."""
+        check(lib.pcq_file_build_index(self.handle))
+
+    def drop_index(self):
+        lib.pcq_file_drop_index(self.handle)
+
+    @property
+    def index(self) -> np.ndarray:
+        """Copy of the chunk headers (CHUNK_HEADER_DTYPE); empty when the file has no index."""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(lib.pcq_file_index(self.handle, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=B.CHUNK_HEADER_DTYPE)
+        raw = C.string_at(p.value, n.value * B.CHUNK_HEADER_DTYPE.itemsize)
+        return np.frombuffer(raw, dtype=B.CHUNK_HEADER_DTYPE).copy()
 
     def release(self):
         if self.handle:

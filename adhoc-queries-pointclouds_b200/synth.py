@@ -148,3 +148,47 @@ def uniform_spec(n_points: int, layout: int, fmt: int, seed: int = 0x5EED0000 + 
     """C5 sweep: uniform points in a cube of `extent` raw units."""
     return make_spec(seed, n_points, layout, fmt, B.SHAPE_UNIFORM, (0, 0, 0), (extent - 1,) * 3, scale, offset,
                      DOC_CLASSES, record_len=record_len)
+
+
+def strips_device(ctx, n_points: int, n_strips: int = 64, layout: int = B.LAYOUT_LAS, fmt: int = 1,
+                  rare_class_every: int = 4, seed: int = 0x5EED0000 + 6000, extent: int = 1_000_000):
+    """One device-resident file in acquisition order (the chunk-index workload): `n_strips` flight strips stored one
+    after the other, strip k covering its own band of x (10 % overlap with its neighbours) over the whole of y;
+    class 6 occurs only in every `rare_class_every`-th strip.  -> (torch uint8 buffer, FileDesc).
+    Harness-side plumbing (torch holds the memory and, for LAST, transposes the records into columns)."""
+    import torch
+
+    R = FORMAT_LEN[fmt]
+    per = n_points // n_strips
+    n_points = per * n_strips
+    dev = f"cuda:{ctx.device}"
+    buf = torch.empty(n_points * R + 256, dtype=torch.uint8, device=dev)
+    w = extent // n_strips
+    lo_all, hi_all = [2**31 - 1] * 3, [-(2**31)] * 3
+    for k in range(n_strips):
+        classes = DOC_CLASSES if k % rare_class_every == 0 else tuple((v, p) for v, p in DOC_CLASSES if v != 6)
+        tot = sum(p for _, p in classes)
+        classes = tuple((v, p / tot) for v, p in classes)
+        x0, x1 = max(0, k * w - w // 20), min(extent - 1, (k + 1) * w + w // 20)
+        sp = make_spec(seed + k, per, B.LAYOUT_LAS, fmt, B.SHAPE_TERRAIN, (x0, 0, -9488), (x1, extent - 1, 19488),
+                       (0.01,) * 3, (390000.0, 130000.0, 0.0), classes)
+        mm, _ = device_points(ctx, sp, buf.data_ptr() + k * per * R)
+        lo_all = [min(a, b) for a, b in zip(lo_all, mm[:3])]
+        hi_all = [max(a, b) for a, b in zip(hi_all, mm[3:])]
+    whole = make_spec(seed, n_points, layout, fmt, B.SHAPE_TERRAIN, (0, 0, -9488), (extent - 1, extent - 1, 19488),
+                      (0.01,) * 3, (390000.0, 130000.0, 0.0), DOC_CLASSES)
+    mm = (C.c_int32 * 6)(*lo_all, *hi_all)
+    desc = B.FileDesc()
+    check(lib.pcq_synth_desc(C.byref(whole), mm, C.byref(desc)))
+    if layout == B.LAYOUT_LAST:
+        rec = buf[: n_points * R].view(n_points, R)
+        fields = [(0, 12), (12, 2), (14, 1), (15, 1), (16, 1), (17, 1), (18, 2)]
+        if fmt in (1, 3):
+            fields.append((20, 8))
+        if fmt in (2, 3):
+            fields.append((20 if fmt == 2 else 28, 6))
+        cols = torch.cat([rec[:, o: o + s].contiguous().view(-1) for o, s in fields])
+        del rec, buf
+        buf = torch.cat([cols, torch.zeros(256, dtype=torch.uint8, device=dev)])
+        del cols
+    return buf, desc

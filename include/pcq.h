@@ -204,6 +204,45 @@ int pcq_search_host_files_multi(pcq_ctx* ctx, const void* const* file_bytes, con
                                 const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
                                 pcq_collector* const* collectors, uint32_t n_collectors_per_query);
 
+/* ---- on-the-fly chunk index ---------------------------------------------------------------------
+ * The reference's own first idea for going faster (improvements.md:3-10): one header per chunk of
+ * points holding the min/max of the queried attributes, consulted by later scans to find the chunks
+ * that can hold a match.  Here a header covers PCQ_INDEX_CHUNK_POINTS consecutive points of a
+ * resident file and holds the integer AABB of their x/y/z fields and a 256-bit set of the class
+ * bytes that occur (the byte the class search compares, las.rs:202-212 / last.rs:245-259).  A search
+ * over an indexed file launches the scan kernels over the surviving runs of chunks only; scan order,
+ * scan indices and therefore every result are exactly those of the full scan.                     */
+#define PCQ_INDEX_CHUNK_POINTS 8192u
+
+typedef struct pcq_chunk_header {
+  int32_t lo[3], hi[3];  /* min / max of the raw i32 x, y, z of the chunk                          */
+  uint32_t cls_bits[8];  /* bit c set iff some point of the chunk has class byte c                 */
+  uint32_t n_points;     /* points in the chunk (the last one may be short)                        */
+  uint32_t pad_;
+} pcq_chunk_header;      /* 64 bytes */
+
+/* Builds the chunk headers of a resident file in one pass over its point data (k_chunk_index) and
+ * keeps a host copy for the per-search filter.  Synchronises the context's stream.  Idempotent.   */
+int pcq_file_build_index(pcq_file* f);
+void pcq_file_drop_index(pcq_file* f);
+/* Host copy of the headers (owned by the file, valid until it is released or the index dropped);
+ * *out_n == 0 when the file has no index. */
+int pcq_file_index(const pcq_file* f, const pcq_chunk_header** out_headers, uint64_t* out_n);
+/* n > 0: pcq_search_files builds the index of a file by itself when it scans it for the (n+1)-th
+ * time ("while scanning first (without an index) …, upon further scans …").  0 (default): never.  */
+int pcq_ctx_set_auto_index(pcq_ctx* ctx, uint32_t after_n_scans);
+
+/* What the last pcq_search_files call of the context skipped. */
+typedef struct pcq_scan_stats {
+  uint64_t points_total;    /* points of the files that passed the per-file checks                 */
+  uint64_t points_scanned;  /* points the kernels were launched over                               */
+  uint64_t chunks_total;    /* chunks of the indexed files among them                              */
+  uint64_t chunks_skipped;
+  uint32_t segments;        /* point ranges of the launch                                          */
+  uint32_t pad_;
+} pcq_scan_stats;
+int pcq_ctx_last_scan_stats(const pcq_ctx* ctx, pcq_scan_stats* out);
+
 /* Pinned host memory helpers for callers that want full-speed staging. */
 int pcq_host_alloc(size_t n_bytes, void** out);
 void pcq_host_free(void* p);

@@ -150,6 +150,30 @@ def search_class(buf: np.ndarray, layout: str, klass: int) -> np.ndarray:
     return _emit(h, xyz, cls, rgb, sel)
 
 
+CHUNK_HEADER_DTYPE = np.dtype(
+    [("lo", "<i4", (3,)), ("hi", "<i4", (3,)), ("cls_bits", "<u4", (8,)), ("n_points", "<u4"), ("pad", "<u4")]
+)
+
+
+def chunk_headers(buf: np.ndarray, layout: str, chunk_points: int = 8192, first: int = 0, count=None) -> np.ndarray:
+    """The chunk headers improvements.md:3-10 proposes (the reference does not implement them): per chunk of
+    consecutive points the min/max of the raw x/y/z fields and the set of the class bytes the class search compares
+    (las.rs:202-212, last.rs:245-259).  Checker of pcq_file_build_index."""
+    h = parse_header(buf, mask_format=True)
+    xyz, cls, _ = _columns(buf, h, layout)
+    n = h["n"] - first if count is None else count
+    xyz, cls = xyz[first: first + n], cls[first: first + n]
+    out = np.zeros((n + chunk_points - 1) // chunk_points, dtype=CHUNK_HEADER_DTYPE)
+    for c in range(out.shape[0]):
+        a, b = c * chunk_points, min((c + 1) * chunk_points, n)
+        out["lo"][c] = xyz[a:b].min(axis=0)
+        out["hi"][c] = xyz[a:b].max(axis=0)
+        for v in np.unique(cls[a:b]):
+            out["cls_bits"][c, int(v) >> 5] |= np.uint32(1 << (int(v) & 31))
+        out["n_points"][c] = b - a
+    return out
+
+
 class SparseGrid:
     """grid_sampling.rs:9-105 with a dict as the HashMap"""
 

@@ -259,3 +259,32 @@ def test_oracle_reproduces_golden_fixtures(pcq):
         for f, e, want in zip(files, exts, golden[name]["counts"]):
             p = npo.search_bounds(f, e, *kw["bounds"]) if "bounds" in kw else npo.search_class(f, e, kw["cls"])
             assert len(p) == want
+
+
+def test_chunk_headers_restatement_is_a_sound_filter():
+    """improvements.md:3-10: a chunk whose header excludes the query holds no match of the per-point search, and the
+    matches found chunk by chunk over the surviving chunks are the matches of the whole file (both layouts)."""
+    rng = np.random.default_rng(3)
+    n, ch = 10_000, 1024
+    xyz = np.stack([np.arange(n) * 7 + rng.integers(-50, 50, n), rng.integers(0, 1000, n), rng.integers(0, 100, n)], axis=1).astype(np.int32)
+    cls = rng.choice(np.array([1, 2, 5], np.uint8), size=n)
+    cls[3 * ch + 5] = 6
+    cls[3 * ch + 9] = 6 | 0x40
+    for layout in ("las", "last"):
+        f = make_file(xyz, cls, fmt=1, layout=layout)
+        h = npo.chunk_headers(f, layout, chunk_points=ch)
+        assert h.shape[0] == 10 and h["n_points"].sum() == n and h["n_points"][-1] == n - 9 * ch
+        assert np.array_equal(h["lo"][2], xyz[2 * ch: 3 * ch].min(axis=0)) and np.array_equal(h["hi"][9], xyz[9 * ch:].max(axis=0))
+        has6 = [(int(r["cls_bits"][0]) >> 6) & 1 for r in h]
+        assert has6 == [0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+        assert (int(h["cls_bits"][3][(6 | 0x40) >> 5]) >> ((6 | 0x40) & 31)) & 1 == 1
+        qmin, qmax = (200.0, -1.0, -1.0), (300.0, 100.0, 100.0)
+        hd = npo.parse_header(f)
+        lo, hi = npo.local_bounds(hd, qmin, qmax)
+        keep = np.all((h["hi"] >= np.array(lo)) & (h["lo"] <= np.array(hi)), axis=1)
+        assert 0 < keep.sum() < 5
+        want = npo.search_bounds(f, layout, qmin, qmax)
+        x = xyz.astype(np.int64)
+        m = np.all((x >= np.array(lo)) & (x <= np.array(hi)), axis=1)
+        assert m.sum() == want.shape[0] > 0
+        assert not m[~np.repeat(keep, ch)[:n]].any()

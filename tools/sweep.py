@@ -53,10 +53,14 @@ def main():
             e1.record(stream)
             ctx.synchronize()
             ts.append(e0.elapsed_time(e1))
+        timed.last = ts
         return statistics.median(ts)
 
     if args.only in ("configs", "c3", "c4"):
         run_configs(pcq, ctx, stream, timed, peak, args)
+        return
+    if args.only == "index":
+        run_index(pcq, ctx, timed, peak, args)
         return
     cases = [("las", 0), ("las", 1), ("las", 2), ("las", 3), ("last", 1), ("last", 3)]
     if args.cases:  # e.g. --cases las:1,last:3
@@ -82,6 +86,7 @@ def main():
                 line = {"layout": ext, "format": fmt, "record_len": R, "query": query, "collector": collector, "variant": vname,
                         "points": N, "matches": matches, "ms": ms, "gpoints_per_s": N / ms / 1e6, "algorithmic_gb": alg / 1e9,
                         "achieved_gbs": alg / ms / 1e6, "frac_of_measured_peak": alg / ms / 1e6 / peak}
+                line["ms_min"], line["ms_max"] = min(timed.last), max(timed.last)
                 if extra:
                     line.update(extra)
                 print(json.dumps(line), flush=True)
@@ -149,6 +154,77 @@ def main():
                     g.close()
         ctx.set_scan_variant(0)
         df.release()
+        del buf
+        torch.cuda.empty_cache()
+
+
+def run_index(pcq, ctx, timed, peak, args):
+    """The on-the-fly chunk index (improvements.md:3-10) on one file in acquisition order: 64 flight
+    strips stored one after the other.  Build cost, then every query with and without the index (same file)."""
+    import time
+
+    import torch
+
+    S, B = pcq.synth, pcq.binding
+    impl = pcq.SearchImplementation.Optimized
+    cases = [("las", 1), ("last", 1)]
+    if args.cases:
+        cases = [(c.split(":")[0], int(c.split(":")[1])) for c in args.cases.split(",")]
+    for ext, fmt in cases:
+        layout = B.LAYOUT_LAS if ext == "las" else B.LAYOUT_LAST
+        buf, desc = S.strips_device(ctx, args.points, 64, layout, fmt)
+        N, R = int(desc.n_points), int(desc.record_len)
+        plain = pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf)
+        indexed = pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf)
+        builds = []
+        for _ in range(3):
+            indexed.drop_index()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            indexed.build_index()  # synchronises: kernel + copy of the headers to the host
+            builds.append((time.perf_counter() - t0) * 1e3)
+        build_bytes = N * (R if ext == "las" else 13)
+        print(json.dumps({"layout": ext, "format": fmt, "points": N, "index": "build", "ms_host_timed": min(builds),
+                          "chunks": int(indexed.index.shape[0]), "algorithmic_gb": build_bytes / 1e9,
+                          "achieved_gbs": build_bytes / min(builds) / 1e6, "frac_of_measured_peak": build_bytes / min(builds) / 1e6 / peak}), flush=True)
+        ox = 390000.0
+        # x bands of the 10 km footprint: 3 % (two strips), 25 %, 100 %
+        boxes = {"x3pct": ((ox + 4000.0, 0.0, -1e4), (ox + 4300.0, 1e7, 1e4)), "x25pct": ((ox + 2000.0, 0.0, -1e4), (ox + 4500.0, 1e7, 1e4)),
+                 "all": ((0.0, 0.0, -1e4), (1e7, 1e7, 1e4))}
+        queries = [(n, pcq.BoundsSearcher(*b), R if ext == "las" else 12) for n, b in boxes.items()]
+        queries += [("class_6_in_every_4th_strip", pcq.ClassSearcher(6), R if ext == "las" else 1),
+                    ("class_19_absent", pcq.ClassSearcher(19), R if ext == "las" else 1)]
+        for name, s, read_b in queries:
+            for cname, make in (("count", lambda: pcq.CountCollector(ctx)), ("buffer", lambda: pcq.BufferCollector(ctx))):
+                if cname == "buffer" and name == "all":
+                    continue
+                res = {}
+                for label, df in (("full", plain), ("indexed", indexed)):
+                    c = make()
+
+                    def run():
+                        c.reset()
+                        s.search_files([df], impl, [c])
+
+                    ms = timed(run)
+                    # the same call timed on the host clock: the chunk filter and the segment table are host work
+                    ctx.synchronize()
+                    t0 = time.perf_counter()
+                    run()
+                    ctx.synchronize()
+                    wall = (time.perf_counter() - t0) * 1e3
+                    st = ctx.last_scan_stats
+                    res[label] = (ms, wall, c.point_count(), st.points_scanned, st.segments, st.chunks_skipped, st.chunks_total)
+                    c.close()
+                assert res["full"][2] == res["indexed"][2], (name, cname, res)
+                fm, im = res["full"], res["indexed"]
+                print(json.dumps({"layout": ext, "format": fmt, "points": N, "query": name, "collector": cname, "matches": fm[2],
+                                  "full_ms": fm[0], "indexed_ms": im[0], "full_wall_ms": fm[1], "indexed_wall_ms": im[1],
+                                  "speedup": fm[0] / im[0], "speedup_wall": fm[1] / im[1], "points_scanned": im[3], "segments": im[4],
+                                  "chunks_skipped": im[5], "chunks_total": im[6],
+                                  "full_frac_of_measured_peak": (N * read_b + (fm[2] * 31 if cname == "buffer" else 0)) / fm[0] / 1e6 / peak}), flush=True)
+        plain.release()
+        indexed.release()
         del buf
         torch.cuda.empty_cache()
 
