@@ -24,6 +24,7 @@ from .searcher import (  # noqa: F401
     CountCollector,
     DeviceFile,
     GridSampledCollector,
+    HostIndex,
     ResultCollector,
     SearchImplementation,
     Searcher,

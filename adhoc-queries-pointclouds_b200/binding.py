@@ -153,6 +153,10 @@ def _load() -> C.CDLL:
         "pcq_file_index": (C.c_int, [vp, P(vp), P(u64)]),
         "pcq_ctx_set_auto_index": (C.c_int, [vp, u32]),
         "pcq_ctx_last_scan_stats": (C.c_int, [vp, P(ScanStats)]),
+        "pcq_host_index_create": (C.c_int, [vp, P(vp)]),
+        "pcq_host_index_destroy": (None, [vp]),
+        "pcq_host_index_info": (C.c_int, [vp, u32, P(u64), P(C.c_int), P(C.c_int)]),
+        "pcq_search_host_files_indexed": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), u32, P(vp), u32, vp]),
         "pcq_host_alloc": (C.c_int, [sz, P(vp)]),
         "pcq_host_free": (None, [vp]),
         "pcq_grid_export_candidates": (C.c_int, [vp, u32, P(vp), P(u64)]),

@@ -92,6 +92,9 @@ struct pcq_ctx {
   size_t bounce_cap = 0;
   cudaEvent_t bounce_done[kChunkBuffers] = {nullptr, nullptr, nullptr};
   // chunk index
+  void* index_scratch = nullptr;  // device headers of the file being indexed (grow-only)
+  void* index_bounce = nullptr;   // pinned landing buffer of their copy to the host
+  size_t index_scratch_cap = 0;
   uint32_t auto_index_after = 0;  // 0 = never build one unasked
   pcq_scan_stats stats{};
 };
@@ -111,6 +114,24 @@ struct pcq_file {
   // chunk index (index.cu): host copy of the headers (what the per-search filter walks), scans seen so far
   std::vector<pcq_chunk_header> index;
   uint32_t scans = 0;
+};
+
+// Chunk headers of a list of file images that live in host memory (pcq_search_host_files_indexed).  The two parts of
+// a header are kept apart because a pass only sees the columns its queries made it copy: `box` carries lo/hi, `cls`
+// the class set.  Both arrays are pinned: the device writes them with asynchronous copies behind the scans.
+struct pcq_host_index {
+  pcq_ctx* ctx = nullptr;
+  struct File {
+    uint64_t n_points = 0;
+    uint64_t n_chunks = 0;
+    pcq_chunk_header* box = nullptr;
+    pcq_chunk_header* cls = nullptr;
+    bool has_box = false, has_cls = false;
+  };
+  std::vector<File> files;
+  bool pending = false;  // header copies of the last search may still be in flight on the context's stream
+  pcq_chunk_header* d_scratch = nullptr;
+  uint64_t scratch_chunks = 0;
 };
 
 struct pcq_collector {
@@ -999,6 +1020,8 @@ static void ctx_free(pcq_ctx* ctx) {
     if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
     if (ctx->bounce_done[i]) cudaEventDestroy(ctx->bounce_done[i]);
   }
+  if (ctx->index_scratch) cudaFree(ctx->index_scratch);
+  if (ctx->index_bounce) cudaFreeHost(ctx->index_bounce);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1163,30 +1186,39 @@ int pcq_file_build_index(pcq_file* f) {
   a.record_len = f->desc.layout == PCQ_LAYOUT_LAS ? f->desc.record_len : 12u;
   a.cls_off = cls_offset_in_record(f->desc.format);
   a.align = field_alignment(f->rec, a.record_len);
-  void* d_headers = nullptr;
+  a.parts = kIndexPartBox | kIndexPartCls;
+  // device scratch and pinned landing buffer live in the context and only grow: cudaMalloc / cudaFree per build
+  // cost several times the kernel (274 us for 64 M format-1 records)
   const size_t bytes = (size_t)a.n_chunks * sizeof(pcq_chunk_header);
-  if (cudaMalloc(&d_headers, bytes) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM for chunk headers", bytes);
+  if (ctx->index_scratch_cap < bytes) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->index_scratch) cudaFree(ctx->index_scratch);
+    if (ctx->index_bounce) cudaFreeHost(ctx->index_bounce);
+    ctx->index_scratch = ctx->index_bounce = nullptr;
+    ctx->index_scratch_cap = 0;
+    const size_t cap = round_up(bytes + bytes / 4, 1u << 16);
+    if (cudaMalloc(&ctx->index_scratch, cap) != cudaSuccess || cudaMallocHost(&ctx->index_bounce, cap) != cudaSuccess) {
+      cudaGetLastError();
+      if (ctx->index_scratch) cudaFree(ctx->index_scratch);
+      ctx->index_scratch = nullptr;
+      return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes for chunk headers", cap);
+    }
+    ctx->index_scratch_cap = cap;
   }
   std::vector<pcq_chunk_header> headers;
-  int rc = PCQ_OK;
   try {
     headers.resize(a.n_chunks);
   } catch (const std::bad_alloc&) {
-    rc = fail(PCQ_ERR_NOMEM, "out of host memory for %llu chunk headers", (unsigned long long)a.n_chunks);
+    return fail(PCQ_ERR_NOMEM, "out of host memory for %llu chunk headers", (unsigned long long)a.n_chunks);
   }
-  if (rc == PCQ_OK && launch_chunk_index(a, static_cast<pcq_chunk_header*>(d_headers), ctx->sm_count, ctx->stream) != 0)
-    rc = fail(PCQ_ERR_CUDA, "chunk index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  if (rc == PCQ_OK) {
-    ctx->launches++;
-    cudaError_t e = cudaMemcpyAsync(headers.data(), d_headers, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = fail(PCQ_ERR_CUDA, "chunk index: %s", cudaGetErrorString(e));
-  }
-  cudaFree(d_headers);
-  if (rc == PCQ_OK) f->index.swap(headers);
-  return rc;
+  if (launch_chunk_index(a, static_cast<pcq_chunk_header*>(ctx->index_scratch), ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "chunk index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(ctx->index_bounce, ctx->index_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(headers.data(), ctx->index_bounce, bytes);
+  f->index.swap(headers);
+  return PCQ_OK;
 }
 
 void pcq_file_drop_index(pcq_file* f) {
@@ -1422,6 +1454,7 @@ uint64_t surviving_runs(const pcq_file* f, const pcq_query* q, const SegmentPlan
 }
 
 constexpr uint64_t kIndexJoinGap = 4;        // chunks
+constexpr uint64_t kHostIndexJoinGap = 16;   // host-staged: every run is a PCIe copy of its own, keep them megabytes long
 constexpr size_t kIndexMaxRunsPerFile = 4096;
 
 }  // namespace
@@ -1486,7 +1519,10 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
         st.chunks_skipped += n_chunks;
         continue;
       }
-      if (kept * 10 < n_chunks * 9) {  // below that a fragmented launch saves too little
+      // below 90 % a fragmented launch pays; counting a class in a LAST column (1 byte per point, 41 us for 128 M
+      // points) is over before the tile-scheduled launch over the runs has started unless most of it can go
+      const bool byte_count = query->kind == PCQ_QUERY_CLASS && f->desc.layout == PCQ_LAYOUT_LAST && c->kind == PCQ_COLLECT_COUNT;
+      if (byte_count ? kept * 8 < n_chunks : kept * 10 < n_chunks * 9) {
         whole = false;
         st.chunks_skipped += n_chunks - kept;
         const uint64_t R = f->desc.layout == PCQ_LAYOUT_LAS ? f->desc.record_len : 12u;
@@ -1540,7 +1576,7 @@ void pcq_host_free(void* p) {
 // resident, so the bytes cross PCIe once per batch instead of once per query.
 static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
                              uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
-                             pcq_collector* const* collectors, uint32_t n_collectors) {
+                             pcq_collector* const* collectors, uint32_t n_collectors, pcq_host_index* hix) {
   if (n_queries == 0) return PCQ_OK;
   for (uint32_t q = 0; q < n_queries; ++q)
     RC(check_search_args(ctx, n_files, queries + q, collectors + (size_t)q * n_collectors, n_collectors));
@@ -1601,9 +1637,23 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       if (!ctx->bounce_done[b]) CU(cudaEventCreateWithFlags(&ctx->bounce_done[b], cudaEventDisableTiming));
   }
 
-  struct Piece {
+  if (hix) {
+    if (hix->ctx != ctx) return fail(PCQ_ERR_ARG, "host index belongs to another context");
+    if (hix->pending) {  // the filter below reads headers the last search may still be writing
+      CU(cudaStreamSynchronize(ctx->stream));
+      hix->pending = false;
+    }
+    if (hix->files.empty()) hix->files.resize(n_files);
+    if (hix->files.size() != n_files)
+      return fail(PCQ_ERR_ARG, "host index covers %zu files, this search names %u", hix->files.size(), n_files);
+  }
+
+  struct Run {
+    uint64_t first, n;  // points
+  };
+  struct Piece {  // what one ring buffer holds: runs [run0, run0 + n_runs) of one file, packed back to back
     uint32_t file;
-    uint64_t first, n;
+    uint32_t run0, n_runs;
   };
   struct FilePlan {
     pcq_file_desc d;
@@ -1612,9 +1662,15 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     std::vector<uint64_t> base;     // per query: scan index of the file's point 0 in its collector
     uint32_t lane;
     bool any, need_pos, need_cls, need_rgb;
+    bool build_box, build_cls;      // this pass computes that part of the file's chunk headers
+    double kept_fraction;           // points that cross PCIe / points of the file
   };
   std::vector<FilePlan> fps(n_files);
+  std::vector<Run> runs;
   std::vector<Piece> pieces;
+  std::vector<ChunkRun> cruns;
+  pcq_scan_stats stats{};
+  uint64_t scratch_need = 0;
   for (uint32_t i = 0; i < n_files; ++i) {
     FilePlan& fp = fps[i];
     const int layout = layout_of_ext(exts[i]);
@@ -1626,6 +1682,8 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     fp.plan.resize(n_queries);
     fp.base.resize(n_queries);
     fp.any = fp.need_pos = fp.need_cls = fp.need_rgb = false;
+    fp.build_box = fp.build_cls = false;
+    fp.kept_fraction = 1.0;
     for (uint32_t q = 0; q < n_queries; ++q) {
       pcq_collector* c = collectors[(size_t)q * n_collectors + fp.lane];
       fp.base[q] = c->scan_total;
@@ -1642,19 +1700,106 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       fp.need_rgb |= emit && rgb_offset_in_record(fp.d.format) >= 0;
     }
     if (!fp.any) continue;
+    const uint64_t N = fp.d.n_points;
+    stats.points_total += N;
+
+    // chunk headers of this file: use them when every query of the batch can be filtered, else build what the
+    // columns of this pass allow ("while scanning first (without an index) ...", improvements.md:6)
+    pcq_host_index::File* xf = hix ? &hix->files[i] : nullptr;
+    bool filter = false;
+    if (xf) {
+      if (xf->n_chunks != 0 && xf->n_points != N) {  // another file sits at this position now
+        xf->has_box = xf->has_cls = false;
+        if (xf->box) cudaFreeHost(xf->box);
+        if (xf->cls) cudaFreeHost(xf->cls);
+        xf->box = xf->cls = nullptr;
+      }
+      xf->n_points = N;
+      xf->n_chunks = (N + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS;
+      filter = true;
+      for (uint32_t q = 0; q < n_queries; ++q)
+        if (!fp.plan[q].skip && !(queries[q].kind == PCQ_QUERY_BOUNDS ? xf->has_box : xf->has_cls)) filter = false;
+      if (!filter) {
+        const bool las = layout == PCQ_LAYOUT_LAS;
+        fp.build_box = !xf->has_box && (las || fp.need_pos);
+        fp.build_cls = !xf->has_cls && (las || fp.need_cls);
+        const size_t bytes = (size_t)xf->n_chunks * sizeof(pcq_chunk_header);
+        if (fp.build_box && !xf->box && cudaMallocHost(reinterpret_cast<void**>(&xf->box), bytes) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes for chunk headers", bytes);
+        }
+        if (fp.build_cls && !xf->cls && cudaMallocHost(reinterpret_cast<void**>(&xf->cls), bytes) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes for chunk headers", bytes);
+        }
+      }
+    }
+
     uint64_t per_point = layout == PCQ_LAYOUT_LAS
                              ? fp.d.record_len
                              : (fp.need_pos ? 12 : 0) + (fp.need_cls ? 1 : 0) + (fp.need_rgb ? 6 : 0);
-    uint64_t pts = (chunk_bytes - 1024) / per_point;
-    pts = std::max<uint64_t>(kTilePts, pts / kTilePts * kTilePts);
-    for (uint64_t first = 0; first < fp.d.n_points; first += pts)
-      pieces.push_back({i, first, std::min<uint64_t>(pts, fp.d.n_points - first)});
+    // a run's columns are rounded up to 256 bytes each: three roundings per run at most
+    uint64_t pts = (chunk_bytes - 1024 - 768) / per_point;
+    pts = std::max<uint64_t>(PCQ_INDEX_CHUNK_POINTS, pts / PCQ_INDEX_CHUNK_POINTS * PCQ_INDEX_CHUNK_POINTS);
+    auto run_bytes = [&](uint64_t n) -> uint64_t {
+      if (layout == PCQ_LAYOUT_LAS) return round_up(n * fp.d.record_len, 256);
+      return (fp.need_pos ? round_up(n * 12, 256) : 0) + (fp.need_cls ? round_up(n, 256) : 0) + (fp.need_rgb ? round_up(n * 6, 256) : 0);
+    };
+    cruns.clear();
+    if (filter) {
+      // a chunk crosses PCIe when some query of the batch may find a match in it; short gaps are copied along
+      stats.chunks_total += xf->n_chunks;
+      for (uint64_t c = 0; c < xf->n_chunks; ++c) {
+        bool may = false;
+        for (uint32_t q = 0; q < n_queries && !may; ++q)
+          if (!fp.plan[q].skip)
+            may = chunk_may_match(queries[q].kind == PCQ_QUERY_BOUNDS ? xf->box[c] : xf->cls[c], queries + q, fp.plan[q]);
+        if (!may) continue;
+        if (!cruns.empty() && c - cruns.back().end < kHostIndexJoinGap)
+          cruns.back().end = c + 1;
+        else
+          cruns.push_back({c, c + 1});
+      }
+      uint64_t kept = 0;
+      for (const ChunkRun& r : cruns) kept += r.end - r.first;
+      stats.chunks_skipped += xf->n_chunks - kept;
+    } else {
+      cruns.push_back({0, (N + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS});
+    }
+    uint64_t kept_points = 0;
+    uint64_t room = 0;
+    for (const ChunkRun& r : cruns) {
+      const uint64_t p0 = r.first * PCQ_INDEX_CHUNK_POINTS, p1 = std::min<uint64_t>(r.end * PCQ_INDEX_CHUNK_POINTS, N);
+      for (uint64_t first = p0; first < p1; first += pts) {
+        const uint64_t n = std::min<uint64_t>(pts, p1 - first);
+        const uint64_t need = run_bytes(n);
+        if (pieces.empty() || pieces.back().file != i || need > room) {
+          pieces.push_back({i, (uint32_t)runs.size(), 0});
+          room = chunk_bytes - 1024;
+        }
+        runs.push_back({first, n});
+        pieces.back().n_runs++;
+        room -= need;
+        kept_points += n;
+        scratch_need = std::max<uint64_t>(scratch_need, (n + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS);
+      }
+    }
+    stats.points_scanned += kept_points;
+    fp.kept_fraction = (double)kept_points / (double)N;
+  }
+  if (hix && hix->scratch_chunks < scratch_need) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (hix->d_scratch) cudaFree(hix->d_scratch);
+    hix->d_scratch = nullptr;
+    hix->scratch_chunks = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(&hix->d_scratch), scratch_need * sizeof(pcq_chunk_header)));
+    hix->scratch_chunks = scratch_need;
   }
 
   struct Staged {
     const uint8_t *rec, *cls, *rgb;
   };
-  std::vector<Staged> staged(pieces.size());
+  std::vector<Staged> staged(runs.size());
   bool bounce_used[kChunkBuffers] = {false, false, false};
   auto issue_copy = [&](size_t j) -> int {
     const Piece& pc = pieces[j];
@@ -1664,7 +1809,6 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     uint8_t* dst = static_cast<uint8_t*>(ctx->chunk[b]);
     const uint8_t* src = static_cast<const uint8_t*>(file_bytes[pc.file]) + fp.d.point_data_off;
     const uint64_t N = fp.d.n_points;
-    Staged st{nullptr, nullptr, nullptr};
     const bool via_bounce = pageable[pc.file] != 0;
     uint8_t* hb = via_bounce ? static_cast<uint8_t*>(ctx->bounce[b]) : nullptr;
     if (via_bounce && bounce_used[b]) CU(cudaEventSynchronize(ctx->bounce_done[b]));  // the slot's last H2D has left it
@@ -1678,33 +1822,39 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       }
       return PCQ_OK;
     };
-    if (fp.d.layout == PCQ_LAYOUT_LAS) {
-      RC(put(0, src + pc.first * fp.d.record_len, pc.n * fp.d.record_len));
-      st.rec = dst;
-    } else {
-      size_t o = 0;
-      if (fp.need_pos) {
-        RC(put(o, src + pc.first * 12, pc.n * 12));
+    size_t o = 0;
+    for (uint32_t r = pc.run0; r < pc.run0 + pc.n_runs; ++r) {
+      const Run& rn = runs[r];
+      Staged st{nullptr, nullptr, nullptr};
+      if (fp.d.layout == PCQ_LAYOUT_LAS) {
+        RC(put(o, src + rn.first * fp.d.record_len, rn.n * fp.d.record_len));
         st.rec = dst + o;
-        o += round_up(pc.n * 12, 256);
+        o += round_up(rn.n * fp.d.record_len, 256);
       } else {
-        st.rec = dst;  // never dereferenced by a class count
+        if (fp.need_pos) {
+          RC(put(o, src + rn.first * 12, rn.n * 12));
+          st.rec = dst + o;
+          o += round_up(rn.n * 12, 256);
+        } else {
+          st.rec = dst;  // never dereferenced by a class count
+        }
+        if (fp.need_cls) {
+          RC(put(o, src + (uint64_t)cls_offset_in_record(fp.d.format) * N + rn.first, rn.n));
+          st.cls = dst + o;
+          o += round_up(rn.n, 256);
+        }
+        if (fp.need_rgb) {
+          RC(put(o, src + (uint64_t)rgb_offset_in_record(fp.d.format) * N + rn.first * 6, rn.n * 6));
+          st.rgb = dst + o;
+          o += round_up(rn.n * 6, 256);
+        }
       }
-      if (fp.need_cls) {
-        RC(put(o, src + (uint64_t)cls_offset_in_record(fp.d.format) * N + pc.first, pc.n));
-        st.cls = dst + o;
-        o += round_up(pc.n, 256);
-      }
-      if (fp.need_rgb) {
-        RC(put(o, src + (uint64_t)rgb_offset_in_record(fp.d.format) * N + pc.first * 6, pc.n * 6));
-        st.rgb = dst + o;
-      }
+      staged[r] = st;
     }
     if (via_bounce) {
       CU(cudaEventRecord(ctx->bounce_done[b], ctx->copy_stream));
       bounce_used[b] = true;
     }
-    staged[j] = st;
     CU(cudaEventRecord(ctx->chunk_copied[b], ctx->copy_stream));
     return PCQ_OK;
   };
@@ -1713,7 +1863,7 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
   for (int b = 0; b < kChunkBuffers; ++b) CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   const size_t prefetch = kChunkBuffers - 1;
   for (size_t j = 0; j < std::min(prefetch, pieces.size()); ++j) RC(issue_copy(j));
-  std::vector<Segment> segs(1);
+  std::vector<Segment> segs;
   std::vector<uint64_t> lane_points(n_collectors, 0);
   for (size_t j = 0; j < pieces.size(); ++j) {
     if (j + prefetch < pieces.size()) RC(issue_copy(j + prefetch));
@@ -1723,16 +1873,54 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     CU(cudaStreamWaitEvent(ctx->stream, ctx->chunk_copied[b], 0));
     for (uint32_t q = 0; q < n_queries; ++q) {
       if (fp.plan[q].skip) continue;
-      fill_segment(&segs[0], fp.d, staged[j].rec, staged[j].cls, staged[j].rgb, pc.n, fp.plan[q], fp.lane,
-                   fp.base[q] + pc.first, queries[q].kind);
+      segs.resize(pc.n_runs);
       std::fill(lane_points.begin(), lane_points.end(), 0);
-      lane_points[fp.lane] = pc.n;
+      for (uint32_t k = 0; k < pc.n_runs; ++k) {
+        const Run& rn = runs[pc.run0 + k];
+        const Staged& st = staged[pc.run0 + k];
+        fill_segment(&segs[k], fp.d, st.rec, st.cls, st.rgb, rn.n, fp.plan[q], fp.lane, fp.base[q] + rn.first, queries[q].kind);
+        lane_points[fp.lane] += rn.n;
+      }
       // run_batch indexes lanes by Segment::lane, so hand it the query's full collector array
+      const double fr = expected_match_fraction(fp.d, queries + q);
       RC(run_batch(ctx, segs, queries + q, collectors + (size_t)q * n_collectors, n_collectors, lane_points,
-                   expected_match_fraction(fp.d, queries + q)));
+                   fr < 0.0 ? fr : std::min(1.0, fr / fp.kept_fraction)));
+    }
+    if (fp.build_box || fp.build_cls) {
+      // chunk headers as a by-product: the piece is resident anyway (unfiltered files travel as one run per piece,
+      // starting on a chunk boundary)
+      pcq_host_index::File& xf = hix->files[pc.file];
+      for (uint32_t k = 0; k < pc.n_runs; ++k) {
+        const Run& rn = runs[pc.run0 + k];
+        const Staged& st = staged[pc.run0 + k];
+        ChunkIndexArgs a{};
+        a.rec = st.rec;
+        a.cls = st.cls;
+        a.n_points = rn.n;
+        a.n_chunks = (rn.n + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS;
+        a.layout = fp.d.layout;
+        a.record_len = fp.d.layout == PCQ_LAYOUT_LAS ? fp.d.record_len : 12u;
+        a.cls_off = cls_offset_in_record(fp.d.format);
+        a.align = field_alignment(st.rec, a.record_len);
+        a.parts = (uint8_t)((fp.build_box ? kIndexPartBox : 0) | (fp.build_cls ? kIndexPartCls : 0));
+        if (launch_chunk_index(a, hix->d_scratch, ctx->sm_count, ctx->stream) != 0)
+          return fail(PCQ_ERR_CUDA, "chunk index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->launches++;
+        const size_t c0 = (size_t)(rn.first / PCQ_INDEX_CHUNK_POINTS), bytes = (size_t)a.n_chunks * sizeof(pcq_chunk_header);
+        if (fp.build_box) CU(cudaMemcpyAsync(xf.box + c0, hix->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (fp.build_cls) CU(cudaMemcpyAsync(xf.cls + c0, hix->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      }
     }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }
+  if (hix) {
+    for (uint32_t i = 0; i < n_files; ++i) {
+      if (fps[i].build_box) hix->files[i].has_box = true, hix->pending = true;
+      if (fps[i].build_cls) hix->files[i].has_cls = true, hix->pending = true;
+    }
+  }
+  stats.segments = (uint32_t)runs.size();
+  ctx->stats = stats;
   return PCQ_OK;
 }
 
@@ -1740,14 +1928,54 @@ int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const siz
                           uint32_t n_files, const pcq_query* query, pcq_collector* const* collectors,
                           uint32_t n_collectors) {
   if (!query) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
-  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, query, 1, collectors, n_collectors);
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, query, 1, collectors, n_collectors, nullptr);
 }
 
 int pcq_search_host_files_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
                                 const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
                                 pcq_collector* const* collectors, uint32_t n_collectors_per_query) {
   if (!queries && n_queries) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
-  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query);
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, nullptr);
+}
+
+int pcq_host_index_create(pcq_ctx* ctx, pcq_host_index** out) {
+  if (!ctx || !out) return fail(PCQ_ERR_ARG, "null argument");
+  pcq_host_index* ix = new (std::nothrow) pcq_host_index();
+  if (!ix) return fail(PCQ_ERR_NOMEM, "out of host memory");
+  ix->ctx = ctx;
+  ctx->refs++;
+  *out = ix;
+  return PCQ_OK;
+}
+
+void pcq_host_index_destroy(pcq_host_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->ctx->device);
+  cudaStreamSynchronize(ix->ctx->stream);
+  for (pcq_host_index::File& f : ix->files) {
+    if (f.box) cudaFreeHost(f.box);
+    if (f.cls) cudaFreeHost(f.cls);
+  }
+  if (ix->d_scratch) cudaFree(ix->d_scratch);
+  ctx_unref(ix->ctx);
+  delete ix;
+}
+
+int pcq_host_index_info(pcq_host_index* ix, uint32_t file, uint64_t* n_chunks, int* has_box, int* has_cls) {
+  if (!ix) return fail(PCQ_ERR_ARG, "null index");
+  const bool known = file < ix->files.size();
+  if (n_chunks) *n_chunks = known ? ix->files[file].n_chunks : 0;
+  if (has_box) *has_box = known && ix->files[file].has_box;
+  if (has_cls) *has_cls = known && ix->files[file].has_cls;
+  return PCQ_OK;
+}
+
+int pcq_search_host_files_indexed(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
+                                  const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                                  pcq_collector* const* collectors, uint32_t n_collectors_per_query, pcq_host_index* index) {
+  if (!queries && n_queries) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
+  if (!index) return fail(PCQ_ERR_ARG, "null index");
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, index);
 }
 
 // ---- multi-GPU density exchange --------------------------------------------------------------------

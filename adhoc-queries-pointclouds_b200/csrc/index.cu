@@ -79,13 +79,22 @@ __global__ void __launch_bounds__(kIdxBlock) k_chunk_index(ChunkIndexArgs A, pcq
     } else {
       const uint8_t* base = A.rec + p0 * 12ull;
       const uint8_t* cls = A.cls + p0;
-      if (n == kChunk) {
+      if (A.parts & kIndexPartBox) {
+        if (n == kChunk) {
 #pragma unroll 8
-        for (uint32_t j = 0; j < kChunk / kIdxBlock; ++j) {
-          const uint8_t* p = base + (uint64_t)(j * kIdxBlock + tid) * 12u;
-          e.add(field_i32(p, al), field_i32(p + 4, al), field_i32(p + 8, al));
+          for (uint32_t j = 0; j < kChunk / kIdxBlock; ++j) {
+            const uint8_t* p = base + (uint64_t)(j * kIdxBlock + tid) * 12u;
+            e.add(field_i32(p, al), field_i32(p + 4, al), field_i32(p + 8, al));
+          }
+        } else {
+          for (uint32_t i = tid; i < n; i += kIdxBlock) {
+            const uint8_t* p = base + (uint64_t)i * 12u;
+            e.add(field_i32(p, al), field_i32(p + 4, al), field_i32(p + 8, al));
+          }
         }
-        if ((reinterpret_cast<uintptr_t>(cls) & 15u) == 0) {
+      }
+      if (A.parts & kIndexPartCls) {
+        if (n == kChunk && (reinterpret_cast<uintptr_t>(cls) & 15u) == 0) {
           // class column of a full chunk: 512 16-byte words, two per thread
 #pragma unroll
           for (uint32_t j = 0; j < kChunk / 16u / kIdxBlock; ++j) {
@@ -104,12 +113,6 @@ __global__ void __launch_bounds__(kIdxBlock) k_chunk_index(ChunkIndexArgs A, pcq
         } else {
           for (uint32_t i = tid; i < n; i += kIdxBlock) note_class(s_bits, __ldg(cls + i));
         }
-      } else {
-        for (uint32_t i = tid; i < n; i += kIdxBlock) {
-          const uint8_t* p = base + (uint64_t)i * 12u;
-          e.add(field_i32(p, al), field_i32(p + 4, al), field_i32(p + 8, al));
-          note_class(s_bits, __ldg(cls + i));
-        }
       }
     }
 
@@ -120,6 +123,18 @@ __global__ void __launch_bounds__(kIdxBlock) k_chunk_index(ChunkIndexArgs A, pcq
       if ((tid & 31u) == 0) {
         atomicMin(&s_lo[a], lo);
         atomicMax(&s_hi[a], hi);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && A.parts != (kIndexPartBox | kIndexPartCls)) {
+      // the part this pass has no column for: nothing is known, so nothing may be excluded
+      if (!(A.parts & kIndexPartBox)) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s_lo[a] = INT_MIN, s_hi[a] = INT_MAX;
+      }
+      if (!(A.parts & kIndexPartCls)) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_bits[k] = 0xFFFFFFFFu;
       }
     }
     __syncthreads();

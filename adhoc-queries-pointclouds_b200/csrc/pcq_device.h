@@ -173,7 +173,10 @@ struct ChunkIndexArgs {
   uint32_t cls_off;     // LAS only: the byte the class search compares (15 / 16)
   uint8_t layout;
   uint8_t align;        // alignment of the x/y/z fields: 4, 2 or 1
+  uint8_t parts;        // kIndexPartBox | kIndexPartCls: a LAST pass may hold only one of the two columns; the part
+                        // that is not computed is written as "anything may be here" (full i32 range / every class)
 };
+constexpr uint8_t kIndexPartBox = 1, kIndexPartCls = 2;
 int launch_chunk_index(const ChunkIndexArgs& a, pcq_chunk_header* out, int sm_count, void* stream);
 
 }  // namespace pcq

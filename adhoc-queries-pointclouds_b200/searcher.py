@@ -299,9 +299,39 @@ class Searcher:
         check(lib.pcq_search_host_files(ctx.handle, ptrs, sizes, exts, n, C.byref(q), ch, len(collectors)))
 
 
+class HostIndex:
+    """Chunk headers of a list of host file images (pcq_host_index): built as a by-product of the first host-staged
+    pass, used by later passes to copy only the chunks that can hold a match."""
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(lib.pcq_host_index_create(self.ctx.handle, C.byref(h)))
+        self.handle = h
+
+    def info(self, file: int) -> tuple:
+        """-> (chunks, has AABB part, has class part) of file `file` of the list"""
+        n, hb, hc = C.c_uint64(), C.c_int(), C.c_int()
+        check(lib.pcq_host_index_info(self.handle, int(file), C.byref(n), C.byref(hb), C.byref(hc)))
+        return int(n.value), bool(hb.value), bool(hc.value)
+
+    def close(self):
+        if self.handle:
+            lib.pcq_host_index_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def search_host_files_multi(images: Sequence[tuple], searchers: Sequence["Searcher"],
-                            collectors_per_query: Sequence[Sequence[ResultCollector]]) -> None:
-    """One host-staged pass for several queries (pcq_search_host_files_multi): the file images cross PCIe once."""
+                            collectors_per_query: Sequence[Sequence[ResultCollector]],
+                            index: Optional[HostIndex] = None) -> None:
+    """One host-staged pass for several queries (pcq_search_host_files_multi): the file images cross PCIe once.
+    With `index` (pcq_search_host_files_indexed) only the chunks that can hold a match cross it."""
     ctx = collectors_per_query[0][0].ctx
     n, nq, ncol = len(images), len(searchers), len(collectors_per_query[0])
     assert all(len(c) == ncol for c in collectors_per_query) and len(collectors_per_query) == nq
@@ -311,7 +341,10 @@ def search_host_files_multi(images: Sequence[tuple], searchers: Sequence["Search
     exts = (C.c_char_p * n)(*[e.encode() for _, e in images])
     qs = (B.Query * nq)(*[s._query() for s in searchers])
     ch = (C.c_void_p * (nq * ncol))(*[c.handle for cs in collectors_per_query for c in cs])
-    check(lib.pcq_search_host_files_multi(ctx.handle, ptrs, sizes, exts, n, qs, nq, ch, ncol))
+    if index is not None:
+        check(lib.pcq_search_host_files_indexed(ctx.handle, ptrs, sizes, exts, n, qs, nq, ch, ncol, index.handle))
+    else:
+        check(lib.pcq_search_host_files_multi(ctx.handle, ptrs, sizes, exts, n, qs, nq, ch, ncol))
 
 
 class BoundsSearcher(Searcher):

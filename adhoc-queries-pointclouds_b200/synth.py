@@ -154,7 +154,7 @@ def strips_device(ctx, n_points: int, n_strips: int = 64, layout: int = B.LAYOUT
                   rare_class_every: int = 4, seed: int = 0x5EED0000 + 6000, extent: int = 1_000_000):
     """One device-resident file in acquisition order (the chunk-index workload): `n_strips` flight strips stored one
     after the other, strip k covering its own band of x (10 % overlap with its neighbours) over the whole of y;
-    class 6 occurs only in every `rare_class_every`-th strip.  -> (torch uint8 buffer, FileDesc).
+    class 6 occurs only in every `rare_class_every`-th strip.  -> (torch uint8 buffer, FileDesc, 227-byte header).
     Harness-side plumbing (torch holds the memory and, for LAST, transposes the records into columns)."""
     import torch
 
@@ -191,4 +191,4 @@ def strips_device(ctx, n_points: int, n_strips: int = 64, layout: int = B.LAYOUT
         del rec, buf
         buf = torch.cat([cols, torch.zeros(256, dtype=torch.uint8, device=dev)])
         del cols
-    return buf, desc
+    return buf, desc, header_bytes(whole, list(lo_all) + list(hi_all))

@@ -232,7 +232,8 @@ int pcq_file_index(const pcq_file* f, const pcq_chunk_header** out_headers, uint
  * time ("while scanning first (without an index) …, upon further scans …").  0 (default): never.  */
 int pcq_ctx_set_auto_index(pcq_ctx* ctx, uint32_t after_n_scans);
 
-/* What the last pcq_search_files call of the context skipped. */
+/* What the last pcq_search_files / pcq_search_host_files* call of the context skipped (host-staged:
+ * points_scanned = points that crossed PCIe). */
 typedef struct pcq_scan_stats {
   uint64_t points_total;    /* points of the files that passed the per-file checks                 */
   uint64_t points_scanned;  /* points the kernels were launched over                               */
@@ -242,6 +243,21 @@ typedef struct pcq_scan_stats {
   uint32_t pad_;
 } pcq_scan_stats;
 int pcq_ctx_last_scan_stats(const pcq_ctx* ctx, pcq_scan_stats* out);
+
+/* The same idea for file images that stay in host memory (pcq_search_host_files*): the headers are a
+ * by-product of the first pass — every piece is indexed while it is resident for the scan, only for
+ * the attributes whose columns that pass copies (LAS: both; LAST: positions for bounds queries, the
+ * class column for class queries) — and later passes copy only the runs of chunks in which some
+ * query of the batch can find a match, so fewer bytes cross PCIe.  `index` remembers the files by
+ * position in the list: pass the same list every time.  Results equal pcq_search_host_files_multi. */
+typedef struct pcq_host_index pcq_host_index;
+int pcq_host_index_create(pcq_ctx* ctx, pcq_host_index** out);
+void pcq_host_index_destroy(pcq_host_index* index);
+int pcq_host_index_info(pcq_host_index* index, uint32_t file, uint64_t* n_chunks, int* has_box, int* has_cls);
+int pcq_search_host_files_indexed(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
+                                  const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                                  pcq_collector* const* collectors, uint32_t n_collectors_per_query,
+                                  pcq_host_index* index);
 
 /* Pinned host memory helpers for callers that want full-speed staging. */
 int pcq_host_alloc(size_t n_bytes, void** out);

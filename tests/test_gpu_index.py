@@ -178,7 +178,11 @@ def test_index_with_many_short_runs(pcq, ctx):
         for kind in (orc.COLLECT_COUNT, orc.COLLECT_BUFFER):
             got = search(pcq, ctx, [df], kind, cls=11)
             st = ctx.last_scan_stats
-            assert st.segments == 100 and st.chunks_total == 600 and st.chunks_skipped == 500
+            if layout == "last" and kind == orc.COLLECT_COUNT:
+                # counting a class in a 1-byte column is cheaper whole than fragmented unless > 7/8 can be skipped
+                assert st.segments == 1 and st.chunks_total == 600 and st.chunks_skipped == 0
+            else:
+                assert st.segments == 100 and st.chunks_total == 600 and st.chunks_skipped == 500
             assert_same(kind, got, oracle_run([f], [layout], kind, cls=11))
         df.release()
 
@@ -228,3 +232,86 @@ def test_indexed_density_keeps_scan_order_ties(pcq, ctx):
     pts = got[0].points()
     assert sorted(pts["pos"][:, 0].tolist()) == [40.0, 250.0]
     df.release()
+
+
+# ---- host-staged passes with a host index (pcq_search_host_files_indexed) ---------------------------------------
+def host_pass(pcq, ctx, images, queries, kind, index, grid=None, per_file=False):
+    """one batch of queries over host file images -> list (per query) of collector lists"""
+    searchers = [pcq.BoundsSearcher(*q["bounds"]) if "bounds" in q else pcq.ClassSearcher(q["cls"]) for q in queries]
+    cols = [[new_collector(pcq, ctx, kind, grid) for _ in (images if per_file else [0])] for _ in queries]
+    pcq.search_host_files_multi(images, searchers, cols, index=index)
+    return cols
+
+
+@pytest.mark.parametrize("layout,fmt", [("las", 1), ("las", 3), ("last", 1), ("last", 3)])
+def test_host_index_is_a_by_product_and_later_passes_copy_less(pcq, ctx, layout, fmt, monkeypatch):
+    monkeypatch.setenv("PCQ_CHUNK_MB", "2")  # several pieces per file, several runs per piece
+    rng = np.random.default_rng(90 + fmt + (layout == "last"))
+    hdr = fmt % 2
+    n = 61 * CH + 1234
+    files = [strip_file(rng, n, fmt, layout, hdr), strip_file(rng, 7 * CH, fmt, layout, hdr)]
+    images = [(f, layout) for f in files]
+    exts = [layout, layout]
+    span = n * 40
+    narrow = dict(bounds=xbox(hdr, int(0.40 * span), int(0.45 * span)))
+    two = dict(bounds=xbox(hdr, int(0.80 * span), int(0.82 * span)))
+    scale, offset = HEADERS[hdr]
+    gmin = [offset[0] - 4000 * scale[0], offset[1] - 60_000 * scale[0], offset[2] - 600 * scale[0]]
+    gmax = [offset[0] + (span + 4000) * scale[0], offset[1] + 160_000 * scale[1], offset[2] + 6000 * scale[2]]
+    grid = (gmin, gmax, (gmax[0] - gmin[0]) / 300.0)
+    ix = pcq.HostIndex(ctx)
+    assert ix.info(0) == (0, False, False)
+
+    def check(queries, kind, per_file=False):
+        got = host_pass(pcq, ctx, images, queries, kind, ix, grid=grid, per_file=per_file)
+        st = ctx.last_scan_stats
+        for q, cols in zip(queries, got):
+            assert_same(kind, cols, oracle_run(files, exts, kind, grid=grid, per_file=per_file, **q))
+        return st
+
+    # pass 1, a bounds count: everything crosses PCIe; LAS records carry both attributes, LAST only the positions
+    st = check([narrow], orc.COLLECT_COUNT)
+    assert st.chunks_total == 0 and st.points_scanned == st.points_total == n  # (the small file fails the header test)
+    assert ix.info(0) == (62, True, layout == "las")
+    # pass 2: the same box again, then another one, then both in one batch with output
+    st = check([narrow], orc.COLLECT_COUNT)
+    assert st.chunks_total == 62 and st.chunks_skipped > 40 and st.points_scanned < 0.35 * st.points_total
+    st = check([two], orc.COLLECT_BUFFER)
+    assert st.chunks_skipped > 40
+    st = check([narrow, two], orc.COLLECT_BUFFER, per_file=True)
+    assert st.chunks_skipped > 30 and st.segments >= 2  # two separate runs of the big file
+    st = check([narrow, two], orc.COLLECT_GRID)
+    assert st.chunks_skipped > 30
+    # class queries: LAST has no class part yet -> full pass that builds it, then filtered passes
+    st = check([dict(cls=7)], orc.COLLECT_BUFFER)
+    if layout == "last":
+        assert st.chunks_total == 0 and ix.info(0) == (62, True, True) and ix.info(1) == (7, True, True)  # output needs positions too
+    else:
+        assert st.chunks_skipped > 0
+    st = check([dict(cls=7)], orc.COLLECT_BUFFER, per_file=True)
+    assert 0 < st.chunks_skipped < st.chunks_total
+    st = check([dict(cls=9)], orc.COLLECT_COUNT)
+    assert st.points_scanned == 0 and st.chunks_skipped == st.chunks_total == 69
+    st = check([dict(cls=9), narrow], orc.COLLECT_BUFFER)  # mixed batch: union of what the two queries need
+    assert 0 < st.chunks_skipped < st.chunks_total
+    # an unfiltered pass over the same list (index = None) still gives the same answers
+    got = host_pass(pcq, ctx, images, [narrow], orc.COLLECT_BUFFER, None)
+    assert_same(orc.COLLECT_BUFFER, got[0], oracle_run(files, exts, orc.COLLECT_BUFFER, **narrow))
+    ix.close()
+
+
+def test_host_index_from_pageable_memory_and_list_mismatch(pcq, ctx):
+    rng = np.random.default_rng(123)
+    f = strip_file(rng, 30 * CH + 5, 1, "las", 0)  # a numpy array: pageable memory -> pinned bounce ring
+    ix = pcq.HostIndex(ctx)
+    b = xbox(0, 10 * CH * 40, 12 * CH * 40)
+    want = oracle_run([f], ["las"], orc.COLLECT_BUFFER, bounds=b)
+    for k in range(3):
+        got = host_pass(pcq, ctx, [(f, "las")], [dict(bounds=b)], orc.COLLECT_BUFFER, ix)
+        assert_same(orc.COLLECT_BUFFER, got[0], want)
+        st = ctx.last_scan_stats
+        assert (st.chunks_skipped > 20) == (k > 0)
+    with pytest.raises(pcq.PcqError) as e:
+        host_pass(pcq, ctx, [(f, "las"), (f, "las")], [dict(bounds=b)], orc.COLLECT_COUNT, ix)
+    assert e.value.code == pcq.binding.PCQ_ERR_ARG
+    ix.close()

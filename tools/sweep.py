@@ -172,7 +172,7 @@ def run_index(pcq, ctx, timed, peak, args):
         cases = [(c.split(":")[0], int(c.split(":")[1])) for c in args.cases.split(",")]
     for ext, fmt in cases:
         layout = B.LAYOUT_LAS if ext == "las" else B.LAYOUT_LAST
-        buf, desc = S.strips_device(ctx, args.points, 64, layout, fmt)
+        buf, desc, hdr = S.strips_device(ctx, args.points, 64, layout, fmt)
         N, R = int(desc.n_points), int(desc.record_len)
         plain = pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf)
         indexed = pcq.DeviceFile.wrap(ctx, desc, buf.data_ptr(), keepalive=buf)
@@ -225,7 +225,39 @@ def run_index(pcq, ctx, timed, peak, args):
                                   "full_frac_of_measured_peak": (N * read_b + (fm[2] * 31 if cname == "buffer" else 0)) / fm[0] / 1e6 / peak}), flush=True)
         plain.release()
         indexed.release()
-        del buf
+
+        # ---- the same file as a pinned host image: passes through pcq_search_host_files_indexed ----
+        n_host = min(N, 1 << 26)  # 64 M points (1.9 GB as LAS format 1) keep the pinned allocation modest
+        if n_host != N:
+            del buf
+            torch.cuda.empty_cache()
+            buf, desc, hdr = S.strips_device(ctx, n_host, 64, layout, fmt)
+        body = int(desc.n_points) * R
+        img = torch.empty(227 + body, dtype=torch.uint8).pin_memory()
+        img[:227] = torch.from_numpy(hdr)
+        img[227:].copy_(buf[:body])
+        image = (img.numpy(), ext)
+        per_pt = {"bounds": R if ext == "las" else 12, "class": R if ext == "las" else 1}
+        for name, mk, kind in (("x3pct", lambda: pcq.BoundsSearcher(*boxes["x3pct"]), "bounds"), ("x25pct", lambda: pcq.BoundsSearcher(*boxes["x25pct"]), "bounds"),
+                               ("class_6_in_every_4th_strip", lambda: pcq.ClassSearcher(6), "class")):
+            ix = pcq.HostIndex(ctx)
+            rows = {}
+            for label, index in (("no_index", None), ("first_pass_builds", ix), ("indexed", ix), ("indexed_again", ix)):
+                c = pcq.CountCollector(ctx)
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                pcq.search_host_files_multi([image], [mk()], [[c]], index=index)
+                cnt = c.point_count()
+                wall = (time.perf_counter() - t0) * 1e3
+                st = ctx.last_scan_stats
+                rows[label] = {"ms_wall": wall, "matches": cnt, "points_over_pcie": int(st.points_scanned),
+                               "h2d_gb": st.points_scanned * per_pt[kind] / 1e9, "chunks_skipped": int(st.chunks_skipped)}
+                c.close()
+            assert len({r["matches"] for r in rows.values()}) == 1, rows
+            print(json.dumps({"layout": ext, "format": fmt, "points": int(desc.n_points), "host_staged": True, "query": name, "passes": rows,
+                              "speedup_wall": rows["no_index"]["ms_wall"] / rows["indexed_again"]["ms_wall"]}), flush=True)
+            ix.close()
+        del buf, img
         torch.cuda.empty_cache()
 
 
