@@ -118,20 +118,20 @@ struct pcq_file {
 
 // Chunk headers of a list of file images that live in host memory (pcq_search_host_files_indexed).  The two parts of
 // a header are kept apart because a pass only sees the columns its queries made it copy: `box` carries lo/hi, `cls`
-// the class set.  Both arrays are pinned: the device writes them with asynchronous copies behind the scans.
+// the class set.  A building pass writes the headers of a file into its device array behind the scans; the next
+// indexed search fetches them into the host vectors the filter walks.
 struct pcq_host_index {
   pcq_ctx* ctx = nullptr;
   struct File {
     uint64_t n_points = 0;
     uint64_t n_chunks = 0;
-    pcq_chunk_header* box = nullptr;
-    pcq_chunk_header* cls = nullptr;
+    pcq_chunk_header* d_headers = nullptr;  // n_chunks headers, written by k_chunk_index
+    uint8_t unfetched = 0;                  // parts (kIndexPartBox | kIndexPartCls) of d_headers not yet in the vectors
+    std::vector<pcq_chunk_header> box, cls;
     bool has_box = false, has_cls = false;
   };
   std::vector<File> files;
-  bool pending = false;  // header copies of the last search may still be in flight on the context's stream
-  pcq_chunk_header* d_scratch = nullptr;
-  uint64_t scratch_chunks = 0;
+  bool pending = false;  // some file has unfetched headers (their kernels may still be running)
 };
 
 struct pcq_collector {
@@ -1639,8 +1639,17 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
 
   if (hix) {
     if (hix->ctx != ctx) return fail(PCQ_ERR_ARG, "host index belongs to another context");
-    if (hix->pending) {  // the filter below reads headers the last search may still be writing
+    if (hix->pending) {  // headers the last building pass left on the device
       CU(cudaStreamSynchronize(ctx->stream));
+      std::vector<pcq_chunk_header> tmp;
+      for (pcq_host_index::File& xf : hix->files) {
+        if (!xf.unfetched) continue;
+        tmp.resize(xf.n_chunks);
+        CU(cudaMemcpy(tmp.data(), xf.d_headers, (size_t)xf.n_chunks * sizeof(pcq_chunk_header), cudaMemcpyDeviceToHost));
+        if (xf.unfetched & kIndexPartBox) xf.box = tmp;
+        if (xf.unfetched & kIndexPartCls) xf.cls = tmp;
+        xf.unfetched = 0;
+      }
       hix->pending = false;
     }
     if (hix->files.empty()) hix->files.resize(n_files);
@@ -1670,7 +1679,6 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
   std::vector<Piece> pieces;
   std::vector<ChunkRun> cruns;
   pcq_scan_stats stats{};
-  uint64_t scratch_need = 0;
   for (uint32_t i = 0; i < n_files; ++i) {
     FilePlan& fp = fps[i];
     const int layout = layout_of_ext(exts[i]);
@@ -1710,9 +1718,8 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     if (xf) {
       if (xf->n_chunks != 0 && xf->n_points != N) {  // another file sits at this position now
         xf->has_box = xf->has_cls = false;
-        if (xf->box) cudaFreeHost(xf->box);
-        if (xf->cls) cudaFreeHost(xf->cls);
-        xf->box = xf->cls = nullptr;
+        if (xf->d_headers) cudaFree(xf->d_headers);
+        xf->d_headers = nullptr;
       }
       xf->n_points = N;
       xf->n_chunks = (N + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS;
@@ -1724,13 +1731,9 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
         fp.build_box = !xf->has_box && (las || fp.need_pos);
         fp.build_cls = !xf->has_cls && (las || fp.need_cls);
         const size_t bytes = (size_t)xf->n_chunks * sizeof(pcq_chunk_header);
-        if (fp.build_box && !xf->box && cudaMallocHost(reinterpret_cast<void**>(&xf->box), bytes) != cudaSuccess) {
+        if ((fp.build_box || fp.build_cls) && !xf->d_headers && cudaMalloc(reinterpret_cast<void**>(&xf->d_headers), bytes) != cudaSuccess) {
           cudaGetLastError();
-          return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes for chunk headers", bytes);
-        }
-        if (fp.build_cls && !xf->cls && cudaMallocHost(reinterpret_cast<void**>(&xf->cls), bytes) != cudaSuccess) {
-          cudaGetLastError();
-          return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes for chunk headers", bytes);
+          return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM for chunk headers", bytes);
         }
       }
     }
@@ -1781,21 +1784,11 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
         pieces.back().n_runs++;
         room -= need;
         kept_points += n;
-        scratch_need = std::max<uint64_t>(scratch_need, (n + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS);
       }
     }
     stats.points_scanned += kept_points;
     fp.kept_fraction = (double)kept_points / (double)N;
   }
-  if (hix && hix->scratch_chunks < scratch_need) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (hix->d_scratch) cudaFree(hix->d_scratch);
-    hix->d_scratch = nullptr;
-    hix->scratch_chunks = 0;
-    CU(cudaMalloc(reinterpret_cast<void**>(&hix->d_scratch), scratch_need * sizeof(pcq_chunk_header)));
-    hix->scratch_chunks = scratch_need;
-  }
-
   struct Staged {
     const uint8_t *rec, *cls, *rgb;
   };
@@ -1903,20 +1896,18 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
         a.cls_off = cls_offset_in_record(fp.d.format);
         a.align = field_alignment(st.rec, a.record_len);
         a.parts = (uint8_t)((fp.build_box ? kIndexPartBox : 0) | (fp.build_cls ? kIndexPartCls : 0));
-        if (launch_chunk_index(a, hix->d_scratch, ctx->sm_count, ctx->stream) != 0)
+        if (launch_chunk_index(a, xf.d_headers + rn.first / PCQ_INDEX_CHUNK_POINTS, ctx->sm_count, ctx->stream) != 0)
           return fail(PCQ_ERR_CUDA, "chunk index launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->launches++;
-        const size_t c0 = (size_t)(rn.first / PCQ_INDEX_CHUNK_POINTS), bytes = (size_t)a.n_chunks * sizeof(pcq_chunk_header);
-        if (fp.build_box) CU(cudaMemcpyAsync(xf.box + c0, hix->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (fp.build_cls) CU(cudaMemcpyAsync(xf.cls + c0, hix->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
       }
     }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }
   if (hix) {
     for (uint32_t i = 0; i < n_files; ++i) {
-      if (fps[i].build_box) hix->files[i].has_box = true, hix->pending = true;
-      if (fps[i].build_cls) hix->files[i].has_cls = true, hix->pending = true;
+      pcq_host_index::File& xf = hix->files[i];
+      if (fps[i].build_box) xf.has_box = true, xf.unfetched |= kIndexPartBox, hix->pending = true;
+      if (fps[i].build_cls) xf.has_cls = true, xf.unfetched |= kIndexPartCls, hix->pending = true;
     }
   }
   stats.segments = (uint32_t)runs.size();
@@ -1952,11 +1943,8 @@ void pcq_host_index_destroy(pcq_host_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->ctx->device);
   cudaStreamSynchronize(ix->ctx->stream);
-  for (pcq_host_index::File& f : ix->files) {
-    if (f.box) cudaFreeHost(f.box);
-    if (f.cls) cudaFreeHost(f.cls);
-  }
-  if (ix->d_scratch) cudaFree(ix->d_scratch);
+  for (pcq_host_index::File& f : ix->files)
+    if (f.d_headers) cudaFree(f.d_headers);
   ctx_unref(ix->ctx);
   delete ix;
 }
