@@ -242,7 +242,8 @@ def run_index(pcq, ctx, timed, peak, args):
                                ("class_6_in_every_4th_strip", lambda: pcq.ClassSearcher(6), "class")):
             ix = pcq.HostIndex(ctx)
             rows = {}
-            for label, index in (("no_index", None), ("first_pass_builds", ix), ("indexed", ix), ("indexed_again", ix)):
+            # (the warm-up pass allocates the context's staging ring the first time round)
+            for label, index in (("warm_up", None), ("no_index", None), ("first_pass_builds", ix), ("indexed", ix), ("indexed_again", ix)):
                 c = pcq.CountCollector(ctx)
                 ctx.synchronize()
                 t0 = time.perf_counter()
@@ -254,6 +255,7 @@ def run_index(pcq, ctx, timed, peak, args):
                                "h2d_gb": st.points_scanned * per_pt[kind] / 1e9, "chunks_skipped": int(st.chunks_skipped)}
                 c.close()
             assert len({r["matches"] for r in rows.values()}) == 1, rows
+            del rows["warm_up"]
             print(json.dumps({"layout": ext, "format": fmt, "points": int(desc.n_points), "host_staged": True, "query": name, "passes": rows,
                               "speedup_wall": rows["no_index"]["ms_wall"] / rows["indexed_again"]["ms_wall"]}), flush=True)
             ix.close()
