@@ -24,6 +24,9 @@
 // round-to-nearest intrinsics (__dmul_rn/__dadd_rn/...) and the file is compiled with --fmad=false.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <cstdint>
 
 #include "pcq_device.h"
@@ -249,35 +252,24 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t n) {
 // Store a 31-byte record at an arbitrarily aligned shared-memory address as 7 word stores, one 16-bit
 // store and one byte store (w[j] = record bytes 4j .. 4j+3, top byte of w[7] zero).
 __device__ __forceinline__ void sts_point31(uint8_t* dst, const uint32_t w[8]) {
+  // Every lane of a warp runs the SAME 14 stores (a 4-way `switch` on the alignment made the warp run 36, nine per
+  // group of eight lanes, and the shared-memory pipe is what bounds a dense select): seven aligned words produced by
+  // a funnel shift whose amount depends on the lane, plus predicated 1- and 2-byte stores for the ragged ends.
   const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
   uint8_t* a = dst - o;  // word aligned; record byte i lives at a[o + i]
-  uint32_t* d = reinterpret_cast<uint32_t*>(a);
-  switch (o) {
-    case 0:
+  uint32_t* d = reinterpret_cast<uint32_t*>(a) + (o != 0u ? 1u : 0u);
+  const uint32_t sh = (32u - 8u * o) & 31u;  // o == 0: the words as they are
 #pragma unroll
-      for (int j = 0; j < 7; ++j) d[j] = w[j];
-      *reinterpret_cast<uint16_t*>(a + 28) = (uint16_t)w[7];
-      a[30] = (uint8_t)(w[7] >> 16);
-      break;
-    case 1:
-      a[1] = (uint8_t)w[0];
-      *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)(w[0] >> 8);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 24);
-      break;
-    case 2:
-      *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)w[0];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 16);
-      a[32] = (uint8_t)(w[7] >> 16);
-      break;
-    default:
-      a[3] = (uint8_t)w[0];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) d[j + 1] = __funnelshift_r(w[j], w[j + 1], 8);
-      *reinterpret_cast<uint16_t*>(a + 32) = (uint16_t)(w[7] >> 8);
-      break;
-  }
+  for (int j = 0; j < 7; ++j) d[j] = __funnelshift_r(w[j], w[j + 1], sh);
+  // head: the 4 - o bytes before the first aligned word
+  if (o == 1u) a[1] = (uint8_t)w[0];
+  if (o == 1u || o == 2u) *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)(o == 1u ? w[0] >> 8 : w[0]);
+  if (o == 3u) a[3] = (uint8_t)w[0];
+  // tail: what is left of w[7] (bytes 28..30 of the record) after the last aligned word
+  if (o == 0u) *reinterpret_cast<uint16_t*>(a + 28) = (uint16_t)w[7];
+  if (o == 0u) a[30] = (uint8_t)(w[7] >> 16);
+  if (o == 2u) a[32] = (uint8_t)(w[7] >> 16);
+  if (o == 3u) *reinterpret_cast<uint16_t*>(a + 32) = (uint16_t)(w[7] >> 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1585,6 +1577,104 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_select_bytes, dense units of colourless LAST files: the emit is a gather of 12-byte positions, and with the
+// register path a warp has 64 + 64 records in flight, which at DRAM latency is ~55 G records/s for the GPU.  Here the
+// positions of 128 matches per round are gathered with cp.async into shared memory, one round ahead: up to 256 records
+// in flight per warp and none of them held in registers.  (The class byte of a match is the query's class.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelBRows = 8;
+constexpr int kSelBWarpPts = kSelBRows * 32 * 16;       // 4096
+constexpr int kSelBUnitPts = kSelWarps * kSelBWarpPts;  // 32768
+constexpr int kSelBLag = 2;
+constexpr int kSelBDenseRecs = 128;
+constexpr int kSelBStageBytes = 4096;                                    // 128 * 31 + 15 phase bytes, rounded up
+constexpr int kSelBGatherBytes = kSelBDenseRecs * 12;                    // positions of one round
+constexpr int kSelBWarpSmem = kSelBStageBytes + 2 * kSelBGatherBytes;    // per consumer warp (dynamic)
+static_assert(kSelBStageBytes >= kSelStageBytes, "the register path stages through the same buffer");
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <class IndexOf>
+__device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const IndexOf& index_of, uint32_t warp_pts,
+                                                        uint8_t* stage, uint8_t* gbuf, uint32_t cls) {
+  const uint32_t w = warp_id(), ln = lane_id();
+  const uint32_t mine = U.warp_cnt[w];
+  uint32_t before = 0;
+  for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
+  const unsigned long long out0 = U.out_rec + before;
+  const Segment& S = U.seg;
+  const uint64_t wbase = U.u0 + (uint64_t)w * warp_pts;
+  const uint64_t pol = l2_policy_drop();
+  // lane l gathers, and later composes, matches l, l + 32, l + 64, l + 96 of a round: no other lane reads its slots
+  auto gather = [&](uint32_t base, uint32_t buf) {
+    const uint32_t n = min((uint32_t)kSelBDenseRecs, mine - base);
+    const uint32_t dst0 = smem_u32(gbuf + buf * (uint32_t)kSelBGatherBytes);
+#pragma unroll
+    for (uint32_t j = 0; j < (uint32_t)kSelBDenseRecs / 32u; ++j) {
+      const uint32_t r = ln + 32u * j;
+      if (r < n) {
+        const uint8_t* p = S.rec + (wbase + index_of(base + r)) * 12ull;
+        cp_async4(dst0 + r * 12u, p);
+        cp_async4(dst0 + r * 12u + 4u, p + 4);
+        cp_async4(dst0 + r * 12u + 8u, p + 8);
+      }
+    }
+    cp_async_commit();
+  };
+  gather(0u, 0u);
+  uint32_t buf = 0;
+#pragma unroll 1
+  for (uint32_t base = 0; base < mine; base += (uint32_t)kSelBDenseRecs, buf ^= 1u) {
+    const unsigned long long orec = out0 + base;
+    const unsigned long long g0 = orec * 31ull;
+    const uint32_t phase = (uint32_t)(g0 & 15ull);  // keep global and shared 16-byte phases equal
+    const uint32_t n = min((uint32_t)kSelBDenseRecs, mine - base);
+    if (base + (uint32_t)kSelBDenseRecs < mine) {
+      gather(base + (uint32_t)kSelBDenseRecs, buf ^ 1u);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const int32_t* gp = reinterpret_cast<const int32_t*>(gbuf + buf * (uint32_t)kSelBGatherBytes);
+#pragma unroll
+    for (uint32_t j = 0; j < (uint32_t)kSelBDenseRecs / 32u; ++j) {
+      const uint32_t r = ln + 32u * j;
+      if (r < n) {
+        RawPoint q;
+        q.x = gp[r * 3u];
+        q.y = gp[r * 3u + 1u];
+        q.z = gp[r * 3u + 2u];
+        q.cls = cls;
+        q.r = q.g = q.b = 0u;  // Vector3::new(0, 0, 0), last.rs:152
+        select_compose(S, q, stage + phase + r * 31u);
+      }
+    }
+    __syncwarp();
+    const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
+    const uint32_t nb = (room < (unsigned long long)n ? (uint32_t)room : n) * 31u;
+    if (nb) {
+      uint8_t* gbase = U.out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
+      const uint32_t end = phase + nb;
+      const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;
+      if (phase + ln < (c_first << 4)) stg_u8_h(gbase + phase + ln, stage[phase + ln], pol);
+      const uint4* sv = reinterpret_cast<const uint4*>(stage);
+      uint4* gv = reinterpret_cast<uint4*>(gbase);
+      for (uint32_t c = c_first + ln; c < c_end; c += 32u) stg_v4_h(gv + c, sv[c], pol);
+      const uint32_t tb = (c_end << 4) + ln;
+      if (tb < end) stg_u8_h(gbase + tb, stage[tb], pol);
+    }
+    __syncwarp();  // the staging buffer is reused by the next round / unit
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MODE_SELECT for LAST class queries (last.rs:253-291): the predicate stream is ONE byte per point, so a 2048-point
 // unit would be 2 KB and the kernel would run at the unit rate of the look-back machinery, not at memory speed.
 // Same roles and barriers as k_select, but a unit is 32768 points: every consumer warp owns 4096 consecutive class
@@ -1592,10 +1682,6 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
 // list the warp keeps, per lane and row, the 16-bit match mask and the number of matches before it; the emit finds
 // its r-th match with a binary search over those 256 prefixes and a find-nth-set-bit.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSelBRows = 8;
-constexpr int kSelBWarpPts = kSelBRows * 32 * 16;       // 4096
-constexpr int kSelBUnitPts = kSelWarps * kSelBWarpPts;  // 32768
-constexpr int kSelBLag = 2;
 
 template <int AL>
 __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
@@ -1604,7 +1690,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
   __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];
   __shared__ __align__(8) uint64_t bar_pre[kSelBufs];
   __shared__ __align__(8) uint64_t bar_free[kSelBufs];
-  __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
+  extern __shared__ __align__(16) uint8_t selb_dsm[];  // per consumer warp: staging buffer, two gather buffers
   __shared__ uint16_t m_mask[kSelWarps][kSelBLag + 1][kSelBRows * 32];  // match mask of (row, lane)
   __shared__ uint16_t m_pre[kSelWarps][kSelBLag + 1][kSelBRows * 32];   // matches of the warp before (row, lane)
 
@@ -1693,7 +1779,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
           const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
           return e * 16u + nth_set_bit((uint32_t)mk[e], r - (uint32_t)pr[e]);
         };
-        select_emit_warp<AL>(unit[pb], index_of, (uint32_t)kSelBWarpPts, stage[w]);
+        uint8_t* stage_w = selb_dsm + (size_t)w * kSelBWarpSmem;
+        const SelUnit& EU = unit[pb];
+        const bool plain = AL == 4 && EU.seg.rgb == nullptr;
+        if (plain && EU.warp_cnt[w] > (uint32_t)kSelBDenseRecs)
+          select_emit_warp_gather(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu);
+        else
+          select_emit_warp<AL>(EU, index_of, (uint32_t)kSelBWarpPts, stage_w);
       }
       __syncwarp();
       if (ln == 0) mbar_arrive(&bar_free[pb]);
@@ -1989,13 +2081,20 @@ static int launch_select_t(const ScanParams& p, int sm_count, cudaStream_t st) {
 template <int AL>
 static int launch_select_bytes_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   auto kfn = k_select_bytes<AL>;
+  constexpr size_t smem = (size_t)kSelWarps * kSelBWarpSmem;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kSelThreads, 0) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kSelThreads, smem) != cudaSuccess) return -1;
+  if (std::getenv("PCQ_VERBOSE")) std::fprintf(stderr, "k_select_bytes<%d>: %d CTAs per SM, %zu bytes dynamic shared memory\n", AL, per_sm, smem);
   if (per_sm < 1) per_sm = 1;
   uint64_t g = (uint64_t)sm_count * (uint64_t)per_sm;
   if (g > p.n_tiles) g = p.n_tiles;
   if (g == 0) return 0;
-  kfn<<<(unsigned)g, kSelThreads, 0, st>>>(p);
+  kfn<<<(unsigned)g, kSelThreads, smem, st>>>(p);
   return check_launch();
 }
 template <int R>

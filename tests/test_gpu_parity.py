@@ -169,6 +169,29 @@ def test_last_class_select_multi_unit(pcq, ctx):
     assert same_point_seq(c.points(), want[0].points())
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_last_class_select_dense_colourless(pcq, ctx, fmt):
+    """k_select_bytes' cp.async gather emit (colourless LAST, more than 128 matches in a warp's 4096 points): density
+    varies along the file from 0 to 100 %, so warps of one unit take different paths; ragged tail; small output
+    buffer first (overflow re-run); several files on one collector and one per file."""
+    rng = np.random.default_rng(300 + fmt)
+    files = []
+    for n in (1_000_003, 70_001, 129):
+        xyz = rng.integers(-50_000, 150_000, size=(n, 3), dtype=np.int32)
+        p = np.clip(np.sin(np.arange(n) / 9000.0) * 0.7 + 0.5, 0.0, 1.0)  # match probability along the file
+        cls = np.where(rng.random(n) < p, 2, rng.choice(np.array([1, 5, 6, 2 | 0x40], np.uint8), size=n)).astype(np.uint8)
+        files.append(make_file(xyz, cls, fmt=fmt, scale=HEADERS[1][0], offset=HEADERS[1][1], layout="last", seed=n))
+    exts = ["last"] * 3
+    for per_file in (False, True):
+        for klass in (2, 6):
+            want = oracle_run(files, exts, orc.COLLECT_BUFFER, cls=klass, per_file=per_file)
+            got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_BUFFER, cls=klass, per_file=per_file)
+            assert_same(orc.COLLECT_BUFFER, got, want)
+    want = oracle_run(files, exts, orc.COLLECT_BUFFER, cls=2)
+    got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_BUFFER, cls=2, host_stream=True)
+    assert_same(orc.COLLECT_BUFFER, got, want)
+
+
 @pytest.mark.parametrize("layout,fmt,unit", [("las", 0, 4096), ("las", 1, 3072), ("las", 2, 3072), ("las", 3, 2048),
                                              ("last", 1, 7168), ("last", 3, 7168)])
 def test_select_around_unit_boundaries(pcq, ctx, layout, fmt, unit):
