@@ -1118,6 +1118,26 @@ __device__ __forceinline__ void select_compose(const Segment& S, const RawPoint&
   sts_point31(dst, wd);
 }
 
+// Copy `nb` staged bytes (whole records, so at least 31) to their place in the output: `stage` is the image of the
+// output stream with the same 16-byte phase as global memory, so the body moves as aligned 16-byte chunks, lane l taking
+// chunks l, l + 32, ... (ITERS * 32 of them at most), and the ragged ends as single bytes.
+template <int ITERS>
+__device__ __forceinline__ void select_flush(uint8_t* out, const uint8_t* stage, unsigned long long g0, uint32_t phase,
+                                             uint32_t nb, uint32_t ln, uint64_t pol) {
+  uint8_t* gbase = out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
+  const uint32_t end = phase + nb;
+  const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;  // full 16-byte chunks [c_first, c_end)
+  if (phase + ln < (c_first << 4)) stg_u8_h(gbase + phase + ln, stage[phase + ln], pol);
+  const uint32_t c0 = c_first + ln;
+  const uint4* sv = reinterpret_cast<const uint4*>(stage) + c0;
+  uint4* gv = reinterpret_cast<uint4*>(gbase) + c0;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+    if (c0 + 32u * (uint32_t)i < c_end) stg_v4_h(gv + 32 * i, sv[32 * i], pol);
+  const uint32_t tb = (c_end << 4) + ln;
+  if (tb < end) stg_u8_h(gbase + tb, stage[tb], pol);
+}
+
 // Emit the matches of consumer warp `w` in unit U (all 32 lanes call it).  index_of(r) is the index, within the
 // warp's `warp_pts` consecutive records of the unit, of the warp's r-th match.  Dense: lane l composes matches l and
 // l + 32 of each round of 64.
@@ -1158,17 +1178,7 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const IndexOf
     // records beyond the lane's capacity are counted but not written (host grows the buffer and re-runs)
     const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
     const uint32_t nb = (room < (unsigned long long)n ? (uint32_t)room : n) * 31u;
-    if (nb) {
-      uint8_t* gbase = U.out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
-      const uint32_t end = phase + nb;
-      const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;  // full 16-byte chunks [c_first, c_end)
-      if (phase + ln < (c_first << 4)) stg_u8_h(gbase + phase + ln, stage[phase + ln], pol);
-      const uint4* sv = reinterpret_cast<const uint4*>(stage);
-      uint4* gv = reinterpret_cast<uint4*>(gbase);
-      for (uint32_t c = c_first + ln; c < c_end; c += 32u) stg_v4_h(gv + c, sv[c], pol);
-      const uint32_t tb = (c_end << 4) + ln;
-      if (tb < end) stg_u8_h(gbase + tb, stage[tb], pol);
-    }
+    if (nb) select_flush<(kSelStageRecs * 31 + 15 + 511) / 512>(U.out, stage, g0, phase, nb, ln, pol);
     __syncwarp();  // the staging buffer is reused by the next round / unit
   }
 }
@@ -1519,7 +1529,8 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
         uint32_t k = 0;  // last row whose first match is not beyond r
 #pragma unroll
         for (int j = 1; j < ROWS; ++j) k += (uint32_t)run[j] <= r ? 1u : 0u;  // run[] is non-decreasing
-        return k * 32u + nth_set_bit(bal[k], r - (uint32_t)run[k]);
+        const uint32_t b = bal[k], n = r - (uint32_t)run[k];
+        return k * 32u + (b == 0xFFFFFFFFu ? n : nth_set_bit(b, n));  // a full row needs no search
       };
       select_emit_warp<AL>(unit[pb], index_of, (uint32_t)WPTS, stage[w]);
     }
@@ -1659,17 +1670,7 @@ __device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const 
     __syncwarp();
     const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
     const uint32_t nb = (room < (unsigned long long)n ? (uint32_t)room : n) * 31u;
-    if (nb) {
-      uint8_t* gbase = U.out + (g0 - phase);  // 16-byte aligned; byte k of `stage` belongs at gbase[k]
-      const uint32_t end = phase + nb;
-      const uint32_t c_first = (phase + 15u) >> 4, c_end = end >> 4;
-      if (phase + ln < (c_first << 4)) stg_u8_h(gbase + phase + ln, stage[phase + ln], pol);
-      const uint4* sv = reinterpret_cast<const uint4*>(stage);
-      uint4* gv = reinterpret_cast<uint4*>(gbase);
-      for (uint32_t c = c_first + ln; c < c_end; c += 32u) stg_v4_h(gv + c, sv[c], pol);
-      const uint32_t tb = (c_end << 4) + ln;
-      if (tb < end) stg_u8_h(gbase + tb, stage[tb], pol);
-    }
+    if (nb) select_flush<(kSelBDenseRecs * 31 + 15 + 511) / 512>(U.out, stage, g0, phase, nb, ln, pol);
     __syncwarp();  // the staging buffer is reused by the next round / unit
   }
 }
