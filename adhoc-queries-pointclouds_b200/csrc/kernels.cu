@@ -272,6 +272,23 @@ __device__ __forceinline__ void sts_point31(uint8_t* dst, const uint32_t w[8]) {
   if (o == 3u) *reinterpret_cast<uint16_t*>(a + 32) = (uint16_t)(w[7] >> 8);
 }
 
+// the same for a record that goes straight to global memory (density winners)
+__device__ __forceinline__ void stg_point31(uint8_t* dst, const uint32_t w[8]) {
+  const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+  uint8_t* a = dst - o;
+  uint32_t* d = reinterpret_cast<uint32_t*>(a) + (o != 0u ? 1u : 0u);
+  const uint32_t sh = (32u - 8u * o) & 31u;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) d[j] = __funnelshift_r(w[j], w[j + 1], sh);
+  if (o == 1u) a[1] = (uint8_t)w[0];
+  if (o == 1u || o == 2u) *reinterpret_cast<uint16_t*>(a + 2) = (uint16_t)(o == 1u ? w[0] >> 8 : w[0]);
+  if (o == 3u) a[3] = (uint8_t)w[0];
+  if (o == 0u) *reinterpret_cast<uint16_t*>(a + 28) = (uint16_t)w[7];
+  if (o == 0u) a[30] = (uint8_t)(w[7] >> 16);
+  if (o == 2u) a[32] = (uint8_t)(w[7] >> 16);
+  if (o == 3u) *reinterpret_cast<uint16_t*>(a + 32) = (uint16_t)(w[7] >> 8);
+}
+
 // ------------------------------------------------------------------------------------------------
 // decoupled look-back (single pass prefix over tiles of one lane)
 //   descriptor = status << 62 | value;  status 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix
@@ -1926,6 +1943,36 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, u
                             unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points,
                             unsigned long long* out_count) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  if (mode == 2) {
+    // winners -> 31-byte points.  One atomic per warp (not per winner) on the single output counter; a record goes out
+    // as the same 14 stores sts_point31 uses, so the winners of a warp fill one contiguous stretch of the output.
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+      const uint64_t i = i0 + threadIdx.x;
+      bool win = false;
+      if (i < n) {
+        const Candidate& c = g.cands[i];
+        if (c.scan_idx != kCandEmpty && c.pad_[0]) {
+          unsigned long long* cell = g.table + grid_slot(g, c.key, false);
+          const unsigned long long mine = (unsigned long long)c.scan_idx;
+          win = *cell == mine && atomicCAS(cell, mine, mine | (1ull << 63)) == mine;
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, win);
+      if (bal == 0u) continue;
+      const uint32_t leader = (uint32_t)__ffs((int)bal) - 1u;
+      unsigned long long base = 0;
+      if (lane_id() == leader) base = atomicAdd(out_count, (unsigned long long)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, (int)leader);
+      if (win) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(g.cands + i);  // the point sits at byte 24 of the candidate
+        const uint4 a = s4[1], b = s4[2], c3 = s4[3];
+        // bytes 24..54 of the candidate: a.z a.w | b.x b.y b.z b.w | c3.x c3.y (low 3 bytes)
+        const uint32_t w[8] = {a.z, a.w, b.x, b.y, b.z, b.w, c3.x, c3.y & 0x00FFFFFFu};
+        stg_point31(out_points + (base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u))) * 31ull, w);
+      }
+    }
+    return;
+  }
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Candidate& c = g.cands[i];
     if (c.scan_idx == kCandEmpty || !c.pad_[0]) continue;
@@ -1937,7 +1984,7 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, u
       if (*cell != mine) continue;
       if (atomicCAS(cell, mine, claimed) != mine) continue;
       atomicAdd(part_counts + (uint32_t)(mix64(c.key) % n_parts), 1ull);
-    } else if (mode == 1) {
+    } else {
       // second walk after mode 0: claimed entries carry bit 63; release the claim while emitting
       if (*cell != claimed) continue;
       if (atomicCAS(cell, claimed, mine) != claimed) continue;
@@ -1949,13 +1996,6 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, u
       o4[1] = s4[1];
       o4[2] = s4[2];
       o4[3] = s4[3];
-    } else {
-      if (*cell != mine) continue;
-      if (atomicCAS(cell, mine, claimed) != mine) continue;
-      const unsigned long long o = atomicAdd(out_count, 1ull);
-      uint8_t* dst = out_points + o * 31ull;
-#pragma unroll
-      for (int b = 0; b < 31; ++b) dst[b] = c.point[b];
     }
   }
 }
