@@ -29,6 +29,7 @@ from .searcher import (  # noqa: F401
     SearchImplementation,
     Searcher,
     default_context,
+    index_filter,
     run_search_parallel,
     run_search_sequential,
     search_host_files_multi,

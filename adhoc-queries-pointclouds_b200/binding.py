@@ -151,6 +151,7 @@ def _load() -> C.CDLL:
         "pcq_file_build_index": (C.c_int, [vp]),
         "pcq_file_drop_index": (None, [vp]),
         "pcq_file_index": (C.c_int, [vp, P(vp), P(u64)]),
+        "pcq_index_filter": (C.c_int, [vp, u64, P(FileDesc), P(Query), u64, vp, u64, P(u64), P(u64)]),
         "pcq_ctx_set_auto_index": (C.c_int, [vp, u32]),
         "pcq_ctx_last_scan_stats": (C.c_int, [vp, P(ScanStats)]),
         "pcq_host_index_create": (C.c_int, [vp, P(vp)]),

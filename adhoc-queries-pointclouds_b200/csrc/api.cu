@@ -1438,12 +1438,12 @@ struct ChunkRun {
 
 // Runs of chunks of an indexed file that can hold a match.  Runs less than `gap` chunks apart are joined (scanning a
 // few chunks that cannot match is cheaper than another point range in the launch); returns the chunks that may match.
-uint64_t surviving_runs(const pcq_file* f, const pcq_query* q, const SegmentPlan& plan, uint64_t gap, std::vector<ChunkRun>& runs) {
+uint64_t surviving_runs(const pcq_chunk_header* headers, uint64_t n, const pcq_query* q, const SegmentPlan& plan, uint64_t gap,
+                        std::vector<ChunkRun>& runs) {
   runs.clear();
   uint64_t may = 0;
-  const uint64_t n = f->index.size();
   for (uint64_t c = 0; c < n; ++c) {
-    if (!chunk_may_match(f->index[c], q, plan)) continue;
+    if (!chunk_may_match(headers[c], q, plan)) continue;
     ++may;
     if (!runs.empty() && c - runs.back().end < gap)
       runs.back().end = c + 1;
@@ -1458,6 +1458,28 @@ constexpr uint64_t kHostIndexJoinGap = 16;   // host-staged: every run is a PCIe
 constexpr size_t kIndexMaxRunsPerFile = 4096;
 
 }  // namespace
+
+int pcq_index_filter(const pcq_chunk_header* headers, uint64_t n_chunks, const pcq_file_desc* desc, const pcq_query* query,
+                     uint64_t join_gap, uint64_t* runs, uint64_t cap_runs, uint64_t* n_runs, uint64_t* n_may) {
+  if ((!headers && n_chunks) || !desc || !query || !n_runs || (!runs && cap_runs)) return fail(PCQ_ERR_ARG, "null argument");
+  if (query->kind == PCQ_QUERY_BOUNDS)
+    for (int i = 0; i < 3; ++i)
+      if (query->qmin[i] > query->qmax[i]) return fail(PCQ_ERR_PANIC, "AABB::from_min_max: query bounds have min > max on axis %d", i);
+  *n_runs = 0;
+  if (n_may) *n_may = 0;
+  SegmentPlan plan;
+  RC(plan_file(*desc, desc->format, query, &plan));
+  if (plan.skip) return PCQ_OK;  // the file's header already excludes the query (las.rs:82-84)
+  std::vector<ChunkRun> found;
+  const uint64_t may = surviving_runs(headers, n_chunks, query, plan, join_gap ? join_gap : 1, found);
+  if (n_may) *n_may = may;
+  *n_runs = found.size();
+  for (size_t i = 0; i < found.size() && i < cap_runs; ++i) {
+    runs[2 * i] = found[i].first;
+    runs[2 * i + 1] = found[i].end;
+  }
+  return PCQ_OK;
+}
 
 static int check_search_args(pcq_ctx* ctx, uint32_t n_files, const pcq_query* q, pcq_collector* const* collectors,
                              uint32_t n_collectors) {
@@ -1510,8 +1532,8 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     if (!f->index.empty()) {
       const uint64_t n_chunks = f->index.size();
       uint64_t gap = kIndexJoinGap;
-      const uint64_t may = surviving_runs(f, query, plan, gap, runs);
-      while (runs.size() > kIndexMaxRunsPerFile) surviving_runs(f, query, plan, gap *= 4, runs);
+      const uint64_t may = surviving_runs(f->index.data(), n_chunks, query, plan, gap, runs);
+      while (runs.size() > kIndexMaxRunsPerFile) surviving_runs(f->index.data(), n_chunks, query, plan, gap *= 4, runs);
       uint64_t kept = 0;
       for (const ChunkRun& r : runs) kept += r.end - r.first;
       st.chunks_total += n_chunks;

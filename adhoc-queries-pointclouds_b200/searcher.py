@@ -299,6 +299,18 @@ class Searcher:
         check(lib.pcq_search_host_files(ctx.handle, ptrs, sizes, exts, n, C.byref(q), ch, len(collectors)))
 
 
+def index_filter(headers: np.ndarray, desc: B.FileDesc, searcher: "Searcher", join_gap: int = 1):
+    """pcq_index_filter (host only): -> (runs as an (n, 2) array of [first_chunk, end_chunk), chunks that may match)"""
+    headers = np.ascontiguousarray(headers, dtype=B.CHUNK_HEADER_DTYPE)
+    cap = max(1, headers.shape[0])
+    runs = np.zeros((cap, 2), dtype=np.uint64)
+    n_runs, n_may = C.c_uint64(), C.c_uint64()
+    q = searcher._query()
+    check(lib.pcq_index_filter(C.c_void_p(headers.ctypes.data), headers.shape[0], C.byref(desc), C.byref(q), int(join_gap),
+                               C.c_void_p(runs.ctypes.data), cap, C.byref(n_runs), C.byref(n_may)))
+    return runs[: n_runs.value].astype(np.int64), int(n_may.value)
+
+
 class HostIndex:
     """Chunk headers of a list of host file images (pcq_host_index): built as a by-product of the first host-staged
     pass, used by later passes to copy only the chunks that can hold a match."""

@@ -228,6 +228,13 @@ void pcq_file_drop_index(pcq_file* f);
 /* Host copy of the headers (owned by the file, valid until it is released or the index dropped);
  * *out_n == 0 when the file has no index. */
 int pcq_file_index(const pcq_file* f, const pcq_chunk_header** out_headers, uint64_t* out_n);
+/* The filter the searches apply, as a host-only function (no GPU): the runs [first_chunk, end_chunk) of chunks of a
+ * file in which `query` can find a match, runs less than `join_gap` chunks apart joined.  Writes the first `cap_runs`
+ * runs as pairs into `runs`, their total number into *n_runs and the number of chunks that may match into *n_may.
+ * Zero runs when the file's header box already excludes the query. */
+int pcq_index_filter(const pcq_chunk_header* headers, uint64_t n_chunks, const pcq_file_desc* desc,
+                     const pcq_query* query, uint64_t join_gap, uint64_t* runs, uint64_t cap_runs,
+                     uint64_t* n_runs, uint64_t* n_may);
 /* n > 0: pcq_search_files builds the index of a file by itself when it scans it for the (n+1)-th
  * time ("while scanning first (without an index) …, upon further scans …").  0 (default): never.  */
 int pcq_ctx_set_auto_index(pcq_ctx* ctx, uint32_t after_n_scans);

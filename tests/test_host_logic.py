@@ -186,3 +186,72 @@ def test_doc_tiles_cover_the_xl_box_and_boxes_select_tiles(pcq):
             if x0 <= qmax[0] and x1 >= qmin[0] and y0 <= qmax[1] and y1 >= qmin[1]:
                 hits[name] += 1
     assert hits == {"S": 5, "L": 30, "XL": 64}
+
+
+# ---- chunk index: the host-side filter (pcq_index_filter) against the per-point search of the oracle --------------
+def _strip_file(rng, n, layout, ch):
+    from tests.helpers import make_file
+
+    i = np.arange(n)
+    xyz = np.stack([i * 40 + rng.integers(-3000, 3000, n), rng.integers(-50_000, 150_000, n), rng.integers(-500, 5000, n)], axis=1).astype(np.int32)
+    cls = rng.choice(np.array([1, 2, 2, 5, 6 | 0x20], np.uint8), size=n)
+    cls[((i // ch) % 7 == 3) & (rng.random(n) < 0.02)] = 6  # class 6 only in every 7th chunk
+    return make_file(xyz, cls, fmt=1, scale=(0.01, 0.01, 0.01), offset=(390000.0, 130000.0, 0.0), layout=layout, seed=5), xyz, cls
+
+
+@pytest.mark.parametrize("layout", ["las", "last"])
+def test_index_filter_is_sound_and_joins_runs(pcq, layout):
+    from oracle import np_oracle as npo
+
+    ch = pcq.binding.INDEX_CHUNK_POINTS
+    rng = np.random.default_rng(17)
+    n = 40 * ch + 321
+    f, xyz, cls = _strip_file(rng, n, layout, ch)
+    headers = npo.chunk_headers(f, layout, chunk_points=ch)
+    desc = _desc(pcq, f, 0 if layout == "las" else 1, 1)
+    n_chunks = headers.shape[0]
+    assert n_chunks == 41
+
+    def chunks_of(runs):
+        keep = np.zeros(n_chunks, dtype=bool)
+        for a, b in runs:
+            assert 0 <= a < b <= n_chunks
+            keep[a:b] = True
+        return keep
+
+    # bounds: a slab in x; every chunk that holds a match of the per-point search must be inside a run
+    for x0, x1 in ((5.2 * ch * 40, 7.9 * ch * 40), (0, 1), (-1e9, 1e9), (39.5 * ch * 40, 1e9)):
+        qmin, qmax = (390000.0 + x0 * 0.01, 0.0, -1e6), (390000.0 + x1 * 0.01, 1e7, 1e6)
+        s = pcq.BoundsSearcher(qmin, qmax)
+        runs, may = pcq.index_filter(headers, desc, s, join_gap=1)
+        hd = npo.parse_header(f)
+        lo, hi = npo.local_bounds(hd, qmin, qmax)
+        m = np.all((xyz.astype(np.int64) >= np.array(lo)) & (xyz.astype(np.int64) <= np.array(hi)), axis=1)
+        assert m.sum() == npo.search_bounds(f, layout, qmin, qmax).shape[0]
+        keep = chunks_of(runs)
+        assert keep.sum() == may
+        assert not m[~np.repeat(keep, ch)[:n]].any(), "a matching point lies in a chunk the filter dropped"
+        if x1 - x0 < 3 * ch * 40:
+            assert 0 < may < 6
+        # runs are maximal and disjoint at gap 1
+        assert all(runs[i][1] < runs[i + 1][0] for i in range(len(runs) - 1))
+    # class: chunks 3, 10, 17, 24, 31, 38 hold class 6; the flag-bit variant 6|0x20 is another byte (las.rs:229)
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(6), join_gap=1)
+    assert may == 6 and [tuple(r) for r in runs] == [(c, c + 1) for c in (3, 10, 17, 24, 31, 38)]
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(6), join_gap=8)   # 7 chunks apart: joined
+    assert may == 6 and [tuple(r) for r in runs] == [(3, 39)]
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(6), join_gap=7)   # gap of 6 chunks < 7: joined too
+    assert [tuple(r) for r in runs] == [(3, 39)]
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(6), join_gap=6)
+    assert len(runs) == 6
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(19), join_gap=4)
+    assert may == 0 and len(runs) == 0
+    runs, may = pcq.index_filter(headers, desc, pcq.ClassSearcher(6 | 0x20), join_gap=4)
+    assert may == n_chunks and [tuple(r) for r in runs] == [(0, n_chunks)]
+    # a query the header box already excludes: no runs at all (the early-out of las.rs:82-84)
+    runs, may = pcq.index_filter(headers, desc, pcq.BoundsSearcher((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)))
+    assert may == 0 and len(runs) == 0
+    # inverted box: the reference panics in AABB::from_min_max
+    with pytest.raises(pcq.PcqError) as e:
+        pcq.index_filter(headers, desc, pcq.BoundsSearcher((5.0, 0.0, 0.0), (1.0, 1.0, 1.0)))
+    assert e.value.code == pcq.binding.PCQ_ERR_PANIC
