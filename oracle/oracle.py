@@ -62,6 +62,7 @@ def _load() -> C.CDLL:
         "orc_collector_point_count": (sz, [vp]),
         "orc_collector_points": (sz, [vp, vp, sz]),
         "orc_search_file": (C.c_int, [vp, sz, C.c_char_p, C.c_int, _D3, _D3, C.c_uint8, vp]),
+        "orc_chunk_headers": (C.c_int, [vp, sz, C.c_char_p, u64, u64, C.c_uint32, vp]),
         "orc_count_parallel": (C.c_int, [P(vp), P(sz), P(C.c_char_p), sz, C.c_int, _D3, _D3, C.c_uint8, C.c_int, P(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -205,3 +206,21 @@ def count_parallel(files, exts, n_threads: int, bounds=None, cls=None) -> np.nda
     if rc != ORC_OK:
         raise OracleError(rc)
     return np.array(list(out), dtype=np.uint64)
+
+
+CHUNK_HEADER_DTYPE = np.dtype(
+    [("lo", "<i4", (3,)), ("hi", "<i4", (3,)), ("cls_bits", "<u4", (8,)), ("n_points", "<u4"), ("pad", "<u4")]
+)
+
+
+def chunk_headers(file_bytes: np.ndarray, ext: str, chunk_points: int = 8192, first: int = 0, count=None) -> np.ndarray:
+    """Chunk headers of the on-the-fly index (improvements.md:3-10), C restatement (orc_chunk_headers)."""
+    if count is None:
+        count = int(parse_header(file_bytes, True).n_points) - first
+    n_chunks = (count + chunk_points - 1) // chunk_points
+    out = np.zeros(n_chunks, dtype=CHUNK_HEADER_DTYPE)
+    rc = lib.orc_chunk_headers(C.c_void_p(file_bytes.ctypes.data), file_bytes.nbytes, ext.encode(), int(first), int(count),
+                               int(chunk_points), C.c_void_p(out.ctypes.data))
+    if rc != ORC_OK:
+        raise OracleError(rc)
+    return out

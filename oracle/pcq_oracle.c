@@ -587,6 +587,54 @@ int orc_search_file(const uint8_t* file, size_t n, const char* ext, int query_ki
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Chunk headers of the on-the-fly index the reference only describes (improvements.md:3-10).
+ * Plain loops over the same fields the searches read: x, y, z i32 at +0/+4/+8 of a record (las.rs:106-119)
+ * or of the positions column (last.rs:114-121); the class byte at +15 / +16 of a record (las.rs:202-212) or
+ * in the class column at off + {15,16} * N (last.rs:245-259).
+ * ------------------------------------------------------------------------------------------- */
+int orc_chunk_headers(const uint8_t* file, size_t n, const char* ext, uint64_t first, uint64_t count,
+                      uint32_t chunk_points, uint32_t* out) {
+  const int is_las = strcmp(ext, "las") == 0;
+  if (!is_las && strcmp(ext, "last") != 0) return ORC_ERR_FORMAT;
+  if (chunk_points == 0) return ORC_ERR_FORMAT;
+  orc_header h;
+  int rc = orc_parse_header(file, n, 1, &h);
+  if (rc != 0) return rc;
+  const uint64_t N = h.n_points;
+  if (first > N || count > N - first) return ORC_ERR_FORMAT;
+  const uint64_t off = h.offset_to_point_data;
+  const uint8_t fmt = (uint8_t)(h.format & 0x0F);
+  const uint64_t cls_k = fmt <= 5 ? 15u : 16u;
+  const uint64_t R = h.record_len;
+  const uint64_t n_chunks = (count + chunk_points - 1) / chunk_points;
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    uint32_t* o = out + 16 * c;
+    int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    uint32_t bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint64_t a = first + c * chunk_points;
+    const uint64_t b = a + chunk_points < first + count ? a + chunk_points : first + count;
+    for (uint64_t i = a; i < b; ++i) {
+      const uint8_t* p = is_las ? file + off + i * R : file + off + i * 12u;
+      const uint8_t k = is_las ? file[off + i * R + cls_k] : file[off + cls_k * N + i];
+      for (int ax = 0; ax < 3; ++ax) {
+        const int32_t v = rd_i32(p + 4 * ax);
+        if (v < lo[ax]) lo[ax] = v;
+        if (v > hi[ax]) hi[ax] = v;
+      }
+      bits[k >> 5] |= 1u << (k & 31u);
+    }
+    for (int ax = 0; ax < 3; ++ax) {
+      o[ax] = (uint32_t)lo[ax];
+      o[3 + ax] = (uint32_t)hi[ax];
+    }
+    for (int j = 0; j < 8; ++j) o[6 + j] = bits[j];
+    o[14] = (uint32_t)(b - a);
+    o[15] = 0;
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * run_search_parallel with CountCollector (main.rs:146-183): files.par_iter() — one task per
  * file, a fresh collector per file, counts summed by the caller.
  * ------------------------------------------------------------------------------------------- */

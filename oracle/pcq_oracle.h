@@ -119,6 +119,14 @@ int orc_count_parallel(const uint8_t* const* files, const size_t* sizes, const c
                        size_t n_files, int query_kind, const double qmin[3], const double qmax[3],
                        uint8_t cls, int n_threads, uint64_t* per_file_counts);
 
+/* The chunk headers improvements.md:3-10 proposes (the reference does not implement them): per chunk of
+ * `chunk_points` consecutive points of the range [first, first + count) of a las / last file image, the min / max
+ * of the raw x, y, z fields and the set of the class bytes the class search compares (las.rs:202-212,
+ * last.rs:245-259).  Checker of pcq_file_build_index.  out: ceil(count / chunk_points) headers of 16 u32 each
+ * (lo[3], hi[3] as i32, cls_bits[8], n_points, 0). */
+int orc_chunk_headers(const uint8_t* file, size_t n, const char* ext, uint64_t first, uint64_t count,
+                      uint32_t chunk_points, uint32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

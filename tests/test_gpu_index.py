@@ -70,10 +70,10 @@ def test_chunk_headers_equal_the_restatement(pcq, ctx, layout, fmt, record_len):
         assert df.index.shape[0] == 0
         df.build_index()
         df.build_index()  # idempotent
-        got, want = df.index, npo.chunk_headers(f, layout)
-        assert got.shape == want.shape == ((n + CH - 1) // CH,)
+        got, want, want_c = df.index, npo.chunk_headers(f, layout), orc.chunk_headers(f, layout)
+        assert got.shape == want.shape == want_c.shape == ((n + CH - 1) // CH,)
         for k in ("lo", "hi", "cls_bits", "n_points"):
-            assert np.array_equal(got[k], want[k]), k
+            assert np.array_equal(got[k], want[k]) and np.array_equal(got[k], want_c[k]), k
         df.drop_index()
         assert df.index.shape[0] == 0
         df.release()

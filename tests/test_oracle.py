@@ -288,3 +288,24 @@ def test_chunk_headers_restatement_is_a_sound_filter():
         m = np.all((x >= np.array(lo)) & (x <= np.array(hi)), axis=1)
         assert m.sum() == want.shape[0] > 0
         assert not m[~np.repeat(keep, ch)[:n]].any()
+
+
+@pytest.mark.parametrize("layout,fmt", [("las", 0), ("las", 3), ("las", 6), ("last", 1), ("last", 3), ("last", 6)])
+def test_chunk_headers_c_and_numpy_restatements_agree(layout, fmt):
+    rng = np.random.default_rng(50 + fmt)
+    n, ch = 5000, 512
+    xyz = rng.integers(-(1 << 31), (1 << 31) - 1, size=(n, 3), dtype=np.int64).astype(np.int32)
+    cls = rng.integers(0, 256, size=n).astype(np.uint8)
+    f = make_file(xyz, cls, fmt=fmt, layout=layout, record_len={0: 23, 3: None, 6: None, 1: None}.get(fmt),
+                  version=(1, 4) if fmt >= 6 else (1, 2))
+    a = orc.chunk_headers(f, layout, chunk_points=ch)
+    b = npo.chunk_headers(f, layout, chunk_points=ch)
+    assert a.shape == b.shape == (10,)
+    for k in ("lo", "hi", "cls_bits", "n_points"):
+        assert np.array_equal(a[k], b[k]), k
+    # a point range, as a rank of a sharded search would index it
+    a = orc.chunk_headers(f, layout, chunk_points=ch, first=700, count=1500)
+    b = npo.chunk_headers(f, layout, chunk_points=ch, first=700, count=1500)
+    for k in ("lo", "hi", "cls_bits", "n_points"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["n_points"].tolist() == [512, 512, 476]
