@@ -255,3 +255,81 @@ def test_index_filter_is_sound_and_joins_runs(pcq, layout):
     with pytest.raises(pcq.PcqError) as e:
         pcq.index_filter(headers, desc, pcq.BoundsSearcher((5.0, 0.0, 0.0), (1.0, 1.0, 1.0)))
     assert e.value.code == pcq.binding.PCQ_ERR_PANIC
+
+
+def test_index_filter_property_random_boxes(pcq):
+    """Random boxes (tiny, huge, far outside the i32 range, anisotropic scales where the reference's min-y / min-z quirk
+    inverts the local box): pcq_index_filter either fails exactly where the per-point search fails, or keeps every
+    chunk that holds a match."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle import np_oracle as npo
+    from tests.helpers import make_file
+
+    ch = 256
+    rng = np.random.default_rng(99)
+    n = 20 * ch + 7
+    i = np.arange(n)
+    xyz = np.stack([i * 13 - 20000 + rng.integers(-400, 400, n), rng.integers(-30000, 30000, n), (i % 977) * 31 - 9000], axis=1).astype(np.int32)
+    cls = rng.integers(0, 8, size=n).astype(np.uint8)
+    files = {}
+    for name, scale in (("iso", (0.01, 0.01, 0.01)), ("aniso", (0.001, 0.002, 0.00025))):
+        f = make_file(xyz, cls, fmt=1, scale=scale, offset=(1000.0, -2000.0, 50.0), layout="las", seed=2)
+        files[name] = (f, npo.chunk_headers(f, "las", chunk_points=ch), _desc(pcq, f, 0, 1), npo.parse_header(f))
+    def axis(scale_a, off_a, lo_raw, hi_raw):
+        w0, w1 = off_a + lo_raw * scale_a, off_a + hi_raw * scale_a
+        span = w1 - w0
+        return st.one_of(st.floats(w0 - span, w1 + span), st.floats(-1e13, 1e13), st.sampled_from([off_a, w0, w1, 1e300, -1e300]))
+
+    def corners(scale):
+        return st.tuples(axis(scale[0], 1000.0, -20400, 49000), axis(scale[1], -2000.0, -30000, 30000), axis(scale[2], 50.0, -9000, 21300))
+
+    cases = st.one_of(st.tuples(st.just("iso"), corners((0.01, 0.01, 0.01)), corners((0.01, 0.01, 0.01))),
+                      st.tuples(st.just("aniso"), corners((0.001, 0.002, 0.00025)), corners((0.001, 0.002, 0.00025))))
+    seen = {"panic": 0, "match": 0, "skipped": 0}
+
+    @settings(max_examples=400, deadline=None)
+    @given(cases, st.integers(1, 5))
+    def run(case, gap):
+        which, a, b = case
+        f, headers, desc, hd = files[which]
+        qmin = tuple(min(x, y) for x, y in zip(a, b))
+        qmax = tuple(max(x, y) for x, y in zip(a, b))
+        try:
+            want = npo.search_bounds(f, "las", qmin, qmax)
+            panicked = False
+        except npo.Panic:
+            panicked = True
+        try:
+            runs, may = pcq.index_filter(headers, desc, pcq.BoundsSearcher(qmin, qmax), join_gap=gap)
+        except pcq.PcqError as e:
+            assert panicked and e.code == pcq.binding.PCQ_ERR_PANIC
+            seen["panic"] += 1
+            return
+        assert not panicked
+        keep = np.zeros(headers.shape[0], dtype=bool)
+        for r0, r1 in runs:
+            keep[r0:r1] = True
+        if want.shape[0]:
+            lo, hi = npo.local_bounds(hd, qmin, qmax)
+            x = xyz.astype(np.int64)
+            lo64 = np.array([max(min(int(v), 1 << 62), -(1 << 62)) for v in lo], dtype=np.int64)
+            hi64 = np.array([max(min(int(v), 1 << 62), -(1 << 62)) for v in hi], dtype=np.int64)
+            m = np.all((x >= lo64) & (x <= hi64), axis=1)
+            assert m.sum() == want.shape[0]
+            assert not m[~np.repeat(keep, ch)[:n]].any()
+            seen["match"] += 1
+            seen["skipped"] += int(keep.sum() < headers.shape[0])
+        assert may <= keep.sum()
+
+    run()
+    assert seen["match"] > 30 and seen["skipped"] > 10, seen  # the strategy reaches boxes with matches and with skipped chunks
+    # a box that intersects the anisotropic file but whose local y range inverts (min uses the x scale, las.rs:91-92)
+    f, headers, desc, hd = files["aniso"]
+    qmin, qmax = (990.0, -1990.0, 40.0), (1040.0, -1985.0, 60.0)
+    with pytest.raises(npo.Panic):
+        npo.search_bounds(f, "las", qmin, qmax)
+    with pytest.raises(pcq.PcqError) as e:
+        pcq.index_filter(headers, desc, pcq.BoundsSearcher(qmin, qmax))
+    assert e.value.code == pcq.binding.PCQ_ERR_PANIC
