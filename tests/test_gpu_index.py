@@ -315,3 +315,25 @@ def test_host_index_from_pageable_memory_and_list_mismatch(pcq, ctx):
         host_pass(pcq, ctx, [(f, "las"), (f, "las")], [dict(bounds=b)], orc.COLLECT_COUNT, ix)
     assert e.value.code == pcq.binding.PCQ_ERR_ARG
     ix.close()
+
+
+def test_last_class_count_over_hundreds_of_runs(pcq, ctx):
+    """More than 256 runs: a LAST class count leaves k_class_count_soa (which walks the segments one by one with the
+    whole grid) for the tile-scheduled scan."""
+    rng = np.random.default_rng(8)
+    n_chunks = 9 * 260
+    n = n_chunks * CH
+    xyz = rng.integers(-1000, 1000, size=(n, 3), dtype=np.int32)
+    cls = rng.choice(np.array([1, 2, 5], np.uint8), size=n)
+    idx = np.flatnonzero((np.arange(n) // CH) % 9 == 4)  # class 11 in one chunk out of nine
+    idx = idx[rng.random(idx.shape[0]) < 0.01]
+    cls[idx] = 11
+    f = make_file(xyz, cls, fmt=0, scale=HEADERS[0][0], offset=HEADERS[0][1], layout="last", seed=4)
+    df = pcq.DeviceFile.stage(ctx, f, "last")
+    df.build_index()
+    got = search(pcq, ctx, [df], orc.COLLECT_COUNT, cls=11)
+    st = ctx.last_scan_stats
+    assert st.segments == 260 and st.chunks_total == n_chunks and st.chunks_skipped == n_chunks - 260
+    assert got[0].point_count() == idx.shape[0] > 10_000
+    assert search(pcq, ctx, [df], orc.COLLECT_COUNT, cls=2)[0].point_count() == int((cls == 2).sum())
+    df.release()
