@@ -47,7 +47,11 @@ def oracle_answer(files, exts, kw):
         orc.search_file(f, e, c, **kw)
         counts.append(c.point_count())
         h.update(np.ascontiguousarray(c.points()).view(np.uint8).tobytes())
-    return {"counts": counts, "buffer_sha256": h.hexdigest()}
+    # chunk headers of the on-the-fly index (8192-point chunks; fields lo, hi, cls_bits, n_points, pad = 0), file by file
+    hh = hashlib.sha256()
+    for f, e in zip(files, exts):
+        hh.update(orc.chunk_headers(f, e).tobytes())
+    return {"counts": counts, "buffer_sha256": h.hexdigest(), "chunk_headers_sha256": hh.hexdigest()}
 
 
 def main():

@@ -337,3 +337,24 @@ def test_last_class_count_over_hundreds_of_runs(pcq, ctx):
     assert got[0].point_count() == idx.shape[0] > 10_000
     assert search(pcq, ctx, [df], orc.COLLECT_COUNT, cls=2)[0].point_count() == int((cls == 2).sum())
     df.release()
+
+
+def test_chunk_headers_golden_fixtures(pcq, ctx):
+    """The committed fixtures (tests/golden/scan_golden.json, generator make_golden.py): SHA-256 of the chunk headers of
+    every file of the seeded datasets."""
+    import hashlib
+    import json
+    from pathlib import Path
+
+    from tests.golden.make_golden import CASES, build_case
+
+    golden = json.loads((Path(__file__).parent / "golden" / "scan_golden.json").read_text())
+    for name in CASES:
+        files, exts, _ = build_case(pcq, name)
+        h = hashlib.sha256()
+        for f, e in zip(files, exts):
+            df = pcq.DeviceFile.stage(ctx, f, e)
+            df.build_index()
+            h.update(np.ascontiguousarray(df.index).tobytes())
+            df.release()
+        assert h.hexdigest() == golden[name]["chunk_headers_sha256"], name

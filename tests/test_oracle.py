@@ -255,6 +255,11 @@ def test_oracle_reproduces_golden_fixtures(pcq):
         assert hashlib.sha256(b"".join(f.tobytes() for f in files)).hexdigest() == golden[name]["input_sha256"], "generator drifted"
         got = oracle_answer(files, exts, kw)
         assert got["counts"] == golden[name]["counts"] and got["buffer_sha256"] == golden[name]["buffer_sha256"]
+        assert got["chunk_headers_sha256"] == golden[name]["chunk_headers_sha256"]
+        hh = hashlib.sha256()
+        for f, e in zip(files, exts):
+            hh.update(npo.chunk_headers(f, e).tobytes())  # the numpy restatement produces the same bytes
+        assert hh.hexdigest() == golden[name]["chunk_headers_sha256"]
         # and the independent numpy restatement agrees with the frozen counts
         for f, e, want in zip(files, exts, golden[name]["counts"]):
             p = npo.search_bounds(f, e, *kw["bounds"]) if "bounds" in kw else npo.search_class(f, e, kw["cls"])
