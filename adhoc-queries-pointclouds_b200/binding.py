@@ -162,11 +162,6 @@ def _load() -> C.CDLL:
         "pcq_host_free": (None, [vp]),
         "pcq_grid_export_candidates": (C.c_int, [vp, u32, P(vp), P(u64)]),
         "pcq_grid_import_candidates": (C.c_int, [vp, vp, u64]),
-        "pcq_synth_file_size": (sz, [P(SynthSpec)]),
-        "pcq_synth_host": (C.c_int, [P(SynthSpec), vp, sz]),
-        "pcq_synth_device": (C.c_int, [vp, P(SynthSpec), vp, C.c_int32 * 6]),
-        "pcq_synth_header": (C.c_int, [P(SynthSpec), C.c_int32 * 6, vp]),
-        "pcq_synth_desc": (C.c_int, [P(SynthSpec), C.c_int32 * 6, P(FileDesc)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == an exported symbol is missing
@@ -177,6 +172,41 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+SYNTH_LIB_PATH = _HERE / "libpcq_synth.so"
+
+
+def _load_synth() -> C.CDLL:
+    """include/pcq_synth.h — the synthetic data generator is a library of its own (test / benchmark tooling)."""
+    if not SYNTH_LIB_PATH.exists():
+        raise ImportError(f"{SYNTH_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    sl = C.CDLL(str(SYNTH_LIB_PATH), mode=os.RTLD_LOCAL)
+    vp, u64, sz = C.c_void_p, C.c_uint64, C.c_size_t
+    P = C.POINTER
+    sigs = {
+        "pcq_synth_last_error": (C.c_char_p, []),
+        "pcq_synth_file_size": (sz, [P(SynthSpec)]),
+        "pcq_synth_host": (C.c_int, [P(SynthSpec), vp, sz]),
+        "pcq_synth_host_points": (C.c_int, [P(SynthSpec), u64, u64, vp, C.c_int32 * 6]),
+        "pcq_synth_device_points": (C.c_int, [C.c_int, P(SynthSpec), u64, u64, vp, C.c_int32 * 6]),
+        "pcq_synth_device": (C.c_int, [C.c_int, P(SynthSpec), vp, C.c_int32 * 6]),
+        "pcq_synth_header": (C.c_int, [P(SynthSpec), C.c_int32 * 6, vp]),
+        "pcq_synth_desc": (C.c_int, [P(SynthSpec), C.c_int32 * 6, P(FileDesc)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(sl, name)
+        fn.restype = res
+        fn.argtypes = args
+    sl._pcq_symbols = tuple(sigs)
+    return sl
+
+
+synth_lib = _load_synth()
+
+
+def check_synth(rc: int) -> None:
+    if rc != PCQ_OK:
+        raise PcqError(rc, synth_lib.pcq_synth_last_error().decode("utf-8", "replace"))
 
 
 def check(rc: int) -> None:

@@ -15,8 +15,7 @@
 #include <unordered_set>
 #include <vector>
 
-#include "host_logic.hpp"
-#include "pcq_device.h"
+#include "pcq_internal.hpp"
 
 using namespace pcq;
 
@@ -31,148 +30,7 @@ using namespace pcq;
     if (rc_ != PCQ_OK) return rc_; \
   } while (0)
 
-namespace {
-
-constexpr int kUploadSlots = 8;
-constexpr int kChunkBuffers = 3;
-
-struct UploadSlot {
-  void* host = nullptr;
-  void* dev = nullptr;
-  size_t cap = 0;
-  cudaEvent_t ev = nullptr;
-  bool pending = false;
-};
-
-// device-side scalars of one collector
-struct DevBlock {
-  unsigned long long count;       // matches (COUNT / BUFFER)
-  unsigned long long cand_count;  // GRID: candidates appended (may exceed capacity on overflow)
-  unsigned long long out_count;   // GRID finalisation: winners emitted
-  uint32_t flags;
-  uint32_t pad_;
-  unsigned long long log_count;   // GRID: replay-log entries written by the last launch (affected keys, alias.cu)
-};
-
-size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-}  // namespace
-
-struct pcq_ctx {
-  // files and collectors keep their context alive: pcq_ctx_destroy only marks it closing while any exist
-  int refs = 0;
-  bool closing = false;
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  int variant = 0;
-  uint64_t launches = 0;
-  UploadSlot slots[kUploadSlots];
-  int next_slot = 0;
-  // MODE_SELECT scratch
-  unsigned long long* tile_state = nullptr;  // [0] = ticket, [1..] = descriptors
-  uint64_t tile_state_cap = 0;
-  // scalar blocks of many collectors travel in one copy
-  void* d_gather = nullptr;
-  void* h_gather = nullptr;
-  size_t gather_cap = 0;
-  // GRID export scratch (one export at a time)
-  unsigned long long* part_scratch = nullptr;  // 2 * n_parts counters
-  uint32_t part_scratch_cap = 0;
-  // host-staged streaming
-  cudaStream_t copy_stream = nullptr;
-  void* chunk[kChunkBuffers] = {nullptr, nullptr, nullptr};
-  size_t chunk_cap = 0;
-  cudaEvent_t chunk_copied[kChunkBuffers] = {nullptr, nullptr, nullptr};
-  cudaEvent_t chunk_free[kChunkBuffers] = {nullptr, nullptr, nullptr};
-  // pinned bounce ring for file images in pageable memory (mmap'ed files): host threads copy a piece in, the copy
-  // engine takes it from there at link speed
-  void* bounce[kChunkBuffers] = {nullptr, nullptr, nullptr};
-  size_t bounce_cap = 0;
-  cudaEvent_t bounce_done[kChunkBuffers] = {nullptr, nullptr, nullptr};
-  // chunk index
-  void* index_scratch = nullptr;  // device headers of the file being indexed (grow-only)
-  void* index_bounce = nullptr;   // pinned landing buffer of their copy to the host
-  size_t index_scratch_cap = 0;
-  uint32_t auto_index_after = 0;  // 0 = never build one unasked
-  pcq_scan_stats stats{};
-};
-
-struct pcq_file {
-  pcq_ctx* ctx = nullptr;
-  pcq_file_desc desc{};
-  uint8_t raw_format = 0;
-  uint64_t first_point = 0;  // index inside the file of record 0 of this range
-  uint64_t n_points = 0;     // points in this range
-  void* owned = nullptr;     // device allocation owned by this object (staged files)
-  const uint8_t* rec = nullptr;
-  const uint8_t* cls = nullptr;
-  const uint8_t* rgb = nullptr;
-  bool has_scan_base = false;
-  uint64_t scan_base = 0;
-  // chunk index (index.cu): host copy of the headers (what the per-search filter walks), scans seen so far
-  std::vector<pcq_chunk_header> index;
-  uint32_t scans = 0;
-};
-
-// Chunk headers of a list of file images that live in host memory (pcq_search_host_files_indexed).  The two parts of
-// a header are kept apart because a pass only sees the columns its queries made it copy: `box` carries lo/hi, `cls`
-// the class set.  A building pass writes the headers of a file into its device array behind the scans; the next
-// indexed search fetches them into the host vectors the filter walks.
-struct pcq_host_index {
-  pcq_ctx* ctx = nullptr;
-  struct File {
-    uint64_t n_points = 0;
-    uint64_t n_chunks = 0;
-    pcq_chunk_header* d_headers = nullptr;  // n_chunks headers, written by k_chunk_index
-    uint8_t unfetched = 0;                  // parts (kIndexPartBox | kIndexPartCls) of d_headers not yet in the vectors
-    std::vector<pcq_chunk_header> box, cls;
-    bool has_box = false, has_cls = false;
-  };
-  std::vector<File> files;
-  bool pending = false;  // some file has unfetched headers (their kernels may still be running)
-};
-
-struct pcq_collector {
-  pcq_ctx* ctx = nullptr;
-  int kind = 0;
-  DevBlock* dev = nullptr;
-  uint64_t scan_total = 0;  // points of all files fed so far (scan index of the next file)
-  // BUFFER
-  uint8_t* d_out = nullptr;
-  uint64_t out_len = 0, out_cap = 0;
-  // GRID
-  double gmin[3]{}, gmax[3]{}, cell = 0;
-  uint64_t dims[3]{}, bits[3]{};
-  GridDev grid{};
-  uint64_t cand_len = 0;
-  uint8_t* d_final = nullptr;
-  uint64_t final_cap = 0, final_n = 0;
-  bool final_valid = false;
-  bool table_holds_winners = false;  // finalised in place: the cells of the winners hold scan indices until grid_restore
-  // key-aliasing replay (alias.cu): affected keys in ordinal order, their fold states (host copy is authoritative
-  // between launches), the device-side set and the replay log
-  std::vector<uint64_t> akeys;
-  std::vector<AliasState> astates;
-  unsigned long long* d_akeys = nullptr;
-  uint32_t* d_aord = nullptr;
-  uint64_t a_slots = 0, a_slots_cap = 0;
-  AliasState* d_astates = nullptr;
-  uint64_t d_astates_cap = 0;
-  Candidate* d_log = nullptr;
-  uint64_t log_cap = 0;
-  uint64_t scan_hi = 0;       // end of the highest point range fed so far: the replay needs launches in scan order
-  uint64_t prune_epoch = 0;   // bumped whenever candidates are dropped (prune / rehash)
-  // export scratch
-  Candidate* d_export = nullptr;
-  uint64_t export_cap = 0;
-  // host copy of points()
-  void* h_pts = nullptr;
-  uint64_t h_cap = 0;
-};
-
-namespace {
+namespace pcq {  // (external linkage: group.cu drives several contexts through these, see pcq_internal.hpp)
 
 int use_device(pcq_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
@@ -395,7 +253,9 @@ GridDev grid_view(const pcq_collector* c) {
   g.alias_keys = c->a_slots ? c->d_akeys : nullptr;
   g.alias_ord = c->a_slots ? c->d_aord : nullptr;
   g.alias_slots = c->a_slots;
-  g.log_only = 0;
+  g.log_only = c->log_only_mode ? 1u : 0u;
+  g.own_parts = c->own_parts;
+  g.own_me = c->own_me;
   g.log = c->d_log;
   g.log_count = &c->dev->log_count;
   g.log_cap = c->log_cap;
@@ -612,12 +472,13 @@ int grid_finalize(pcq_collector* c) {
   if (n) {
     CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
     GridDev g = grid_view(c);
+    c->table_holds_winners = true;  // from the first phase on (also if a later launch fails); the distances go back
+                                    // lazily (grid_restore): usually nothing follows
     for (int phase = 0; phase < 3; ++phase)
       if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0)
         return fail(PCQ_ERR_CUDA, "k_grid_final_phase launch failed");
     if (launch_grid_emit(g, n, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count, ctx->sm_count, ctx->stream) != 0)
       return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
-    c->table_holds_winners = true;  // the distances go back lazily (grid_restore): usually nothing follows
     ctx->launches += 4;
     DevBlock b;
     RC(read_devblock(c, &b));
@@ -945,6 +806,31 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     }
     bool any_logged = false;
     for (uint32_t l = 0; l < n_collectors; ++l) any_logged |= blocks[l].log_count != 0;
+    if (collectors[0]->log_only_mode) {
+      // group-wide ordered replay (group.cu): this pass only collects the points of the affected keys; the launch's
+      // log is appended to the collector's raw log, nothing is inserted or folded here
+      for (uint32_t l = 0; l < n_collectors; ++l) {
+        pcq_collector* c = collectors[l];
+        const uint64_t n_log = blocks[l].log_count;
+        if (n_log == 0) continue;
+        if (c->rawlog_cap < c->rawlog_len + n_log) {
+          const uint64_t cap = std::max<uint64_t>((c->rawlog_len + n_log) * 2, 1u << 14);
+          Candidate* nb = nullptr;
+          if (cudaMalloc(&nb, cap * sizeof(Candidate)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PCQ_ERR_NOMEM, "cannot allocate a raw replay log of %llu entries", (unsigned long long)cap);
+          }
+          if (c->rawlog_len) CU(cudaMemcpyAsync(nb, c->d_rawlog, c->rawlog_len * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
+          CU(cudaStreamSynchronize(ctx->stream));
+          if (c->d_rawlog) cudaFree(c->d_rawlog);
+          c->d_rawlog = nb;
+          c->rawlog_cap = cap;
+        }
+        CU(cudaMemcpyAsync(c->d_rawlog + c->rawlog_len, c->d_log, n_log * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
+        c->rawlog_len += n_log;
+      }
+      any_logged = false;
+    }
     if (any_logged) RC(alias_slow_path(ctx, segs, P, variant, R, min_align, collectors, n_collectors, blocks, epoch0, lane_lo));
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
@@ -956,7 +842,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
   return fail(PCQ_ERR_NOMEM, "collector capacity did not converge");
 }
 
-}  // namespace
+}  // namespace pcq
 
 // =================================================================================================
 extern "C" {
@@ -978,7 +864,10 @@ int pcq_ctx_create(int device, pcq_ctx** out) {
   if (!ctx) return fail(PCQ_ERR_NOMEM, "out of host memory");
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(PCQ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   ctx->own_stream = true;
   const char* v = std::getenv("PCQ_SCAN_VARIANT");
   if (v) ctx->variant = std::atoi(v);
@@ -1066,7 +955,8 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
   if (first_point > d.n_points) return fail(PCQ_ERR_ARG, "first_point %llu beyond %llu points", (unsigned long long)first_point, (unsigned long long)d.n_points);
   uint64_t n = std::min<uint64_t>(n_points, d.n_points - first_point);
   const uint64_t N = d.n_points;
-  if ((uint64_t)d.point_data_off + N * (uint64_t)d.record_len > (uint64_t)n_bytes)
+  if ((uint64_t)d.point_data_off > (uint64_t)n_bytes || d.record_len == 0 ||
+      N > ((uint64_t)n_bytes - d.point_data_off) / d.record_len)  // (division: N * record_len may wrap)
     return fail(PCQ_ERR_IO, "file image holds %zu bytes but its header promises %llu points of %u bytes at offset %u",
                 n_bytes, (unsigned long long)N, d.record_len, d.point_data_off);
   pcq_file* f = new (std::nothrow) pcq_file();
@@ -1077,6 +967,7 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
   f->first_point = first_point;
   f->n_points = n;
   const uint8_t* src = static_cast<const uint8_t*>(file_bytes) + d.point_data_off;
+  cudaError_t copy_err = cudaSuccess;
   if (layout == PCQ_LAYOUT_LAS) {
     const size_t bytes = (size_t)n * d.record_len;
     if (cudaMalloc(&f->owned, round_up(bytes, 256) + 256) != cudaSuccess) {
@@ -1084,7 +975,7 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
       delete f;
       return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM", bytes);
     }
-    if (bytes) CU(cudaMemcpyAsync(f->owned, src + first_point * d.record_len, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) copy_err = cudaMemcpyAsync(f->owned, src + first_point * d.record_len, bytes, cudaMemcpyHostToDevice, ctx->stream);
     f->rec = static_cast<const uint8_t*>(f->owned);
   } else {
     // only the columns the path reads travel: positions, classification, colour (last.rs:80-90, 114)
@@ -1099,19 +990,26 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
     }
     uint8_t* base = static_cast<uint8_t*>(f->owned);
     if (n) {
-      CU(cudaMemcpyAsync(base, src + first_point * 12, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-      CU(cudaMemcpyAsync(base + pos_b, src + (uint64_t)cls_offset_in_record(d.format) * N + first_point, (size_t)n,
-                         cudaMemcpyHostToDevice, ctx->stream));
-      if (rgb_k >= 0)
-        CU(cudaMemcpyAsync(base + pos_b + cls_b, src + (uint64_t)rgb_k * N + first_point * 6, (size_t)n * 6,
-                           cudaMemcpyHostToDevice, ctx->stream));
+      copy_err = cudaMemcpyAsync(base, src + first_point * 12, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+      if (copy_err == cudaSuccess)
+        copy_err = cudaMemcpyAsync(base + pos_b, src + (uint64_t)cls_offset_in_record(d.format) * N + first_point, (size_t)n,
+                                   cudaMemcpyHostToDevice, ctx->stream);
+      if (copy_err == cudaSuccess && rgb_k >= 0)
+        copy_err = cudaMemcpyAsync(base + pos_b + cls_b, src + (uint64_t)rgb_k * N + first_point * 6, (size_t)n * 6,
+                                   cudaMemcpyHostToDevice, ctx->stream);
     }
     f->rec = base;
     f->cls = base + pos_b;
     f->rgb = rgb_k >= 0 ? base + pos_b + cls_b : nullptr;
   }
   // the caller may reuse its buffer as soon as we return
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (copy_err == cudaSuccess) copy_err = cudaStreamSynchronize(ctx->stream);
+  if (copy_err != cudaSuccess) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(f->owned);
+    delete f;
+    return fail(PCQ_ERR_CUDA, "staging copy failed: %s", cudaGetErrorString(copy_err));
+  }
   ctx->refs++;
   *out = f;
   return PCQ_OK;
@@ -1333,6 +1231,7 @@ void pcq_collector_destroy(pcq_collector* c) {
   if (c->d_aord) cudaFree(c->d_aord);
   if (c->d_astates) cudaFree(c->d_astates);
   if (c->d_log) cudaFree(c->d_log);
+  if (c->d_rawlog) cudaFree(c->d_rawlog);
   if (c->h_pts) cudaFreeHost(c->h_pts);
   ctx_unref(c->ctx);
   delete c;
@@ -1353,6 +1252,9 @@ int pcq_collector_reset(pcq_collector* c) {
   c->astates.clear();
   c->a_slots = 0;
   c->scan_hi = 0;
+  c->log_only_mode = false;
+  c->rawlog_len = 0;
+  c->own_parts = c->own_me = 0;
   if (c->kind == PCQ_COLLECT_GRID) {
     CU(cudaMemsetAsync(c->grid.table, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
     if (c->grid.hkeys) CU(cudaMemsetAsync(c->grid.hkeys, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
@@ -1596,9 +1498,11 @@ void pcq_host_free(void* p) {
 // overlaps the scan of chunk k.  Replaces mmap + page-fault driven reads (las.rs:24-31).  Several
 // queries can share one pass: every chunk is scanned by each query that needs its file while it is
 // resident, so the bytes cross PCIe once per batch instead of once per query.
-static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
-                             uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
-                             pcq_collector* const* collectors, uint32_t n_collectors, pcq_host_index* hix) {
+}  // extern "C"
+namespace pcq {
+int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
+                      uint32_t n_files, const pcq_query* queries, uint32_t n_queries, pcq_collector* const* collectors,
+                      uint32_t n_collectors, pcq_host_index* hix, const HostRange* ranges) {
   if (n_queries == 0) return PCQ_OK;
   for (uint32_t q = 0; q < n_queries; ++q)
     RC(check_search_args(ctx, n_files, queries + q, collectors + (size_t)q * n_collectors, n_collectors));
@@ -1606,17 +1510,79 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
   if (!file_bytes || !n_bytes || !exts) return fail(PCQ_ERR_ARG, "null argument");
   RC(use_device(ctx));
 
-  // 256 MB pieces keep a PCIe 5 x16 link at ~54 GB/s (64 MB: 53, 16 MB: 49); small inputs get small buffers
+  struct Run {
+    uint64_t first, n;  // points
+  };
+  struct Piece {  // what one ring buffer holds: runs [run0, run0 + n_runs) of one file, packed back to back
+    uint32_t file;
+    uint32_t run0, n_runs;
+  };
+  struct FilePlan {
+    pcq_file_desc d;
+    uint8_t raw;
+    std::vector<SegmentPlan> plan;  // per query
+    std::vector<uint64_t> base;     // per query: scan index of the file's point 0 in its collector
+    uint32_t lane;
+    int layout;
+    bool any, need_pos, need_cls, need_rgb;
+    bool build_box, build_cls;      // this pass computes that part of the file's chunk headers
+    double kept_fraction;           // points that cross PCIe / points of the file
+    uint64_t per_point;             // bytes of a point that cross PCIe
+  };
+  // Pass 1: everything that can fail on a file (header, length, per-query planning) before any collector or
+  // index state is touched, so that a failed call leaves the collectors' scan bases where they were.
+  std::vector<FilePlan> fps(n_files);
+  uint64_t max_per_point = 1;
+  for (uint32_t i = 0; i < n_files; ++i) {
+    FilePlan& fp = fps[i];
+    fp.layout = layout_of_ext(exts[i]);
+    if (fp.layout < 0) return fail(PCQ_ERR_FORMAT, "Unsupported file extension \"%s\"", exts[i] ? exts[i] : "");
+    if (!file_bytes[i]) return fail(PCQ_ERR_ARG, "null file image %u", i);
+    RC(parse_header(file_bytes[i], n_bytes[i], fp.layout, 1, &fp.d, &fp.raw));
+    if ((uint64_t)fp.d.point_data_off > (uint64_t)n_bytes[i] || fp.d.record_len == 0 ||
+        fp.d.n_points > ((uint64_t)n_bytes[i] - fp.d.point_data_off) / fp.d.record_len)
+      return fail(PCQ_ERR_IO, "file image %u is shorter than its header promises", i);
+    fp.lane = n_collectors == 1 ? 0 : i;
+    fp.plan.resize(n_queries);
+    fp.base.assign(n_queries, 0);
+    fp.any = fp.need_pos = fp.need_cls = fp.need_rgb = false;
+    fp.build_box = fp.build_cls = false;
+    fp.kept_fraction = 1.0;
+    for (uint32_t q = 0; q < n_queries; ++q) {
+      const pcq_collector* c = collectors[(size_t)q * n_collectors + fp.lane];
+      RC(plan_file(fp.d, fp.raw, queries + q, &fp.plan[q]));
+      if (fp.plan[q].skip || fp.d.n_points == 0) {
+        fp.plan[q].skip = true;
+        continue;
+      }
+      const bool emit = c->kind != PCQ_COLLECT_COUNT;
+      fp.any = true;
+      fp.need_pos |= queries[q].kind == PCQ_QUERY_BOUNDS || emit;
+      fp.need_cls |= queries[q].kind == PCQ_QUERY_CLASS || emit;
+      fp.need_rgb |= emit && rgb_offset_in_record(fp.d.format) >= 0;
+    }
+    fp.per_point = fp.layout == PCQ_LAYOUT_LAS
+                       ? fp.d.record_len
+                       : (uint64_t)(fp.need_pos ? 12 : 0) + (fp.need_cls ? 1 : 0) + (fp.need_rgb ? 6 : 0);
+    if (fp.any) max_per_point = std::max(max_per_point, fp.per_point);
+  }
+
+  // 256 MB pieces keep a PCIe 5 x16 link at ~54 GB/s (64 MB: 53, 16 MB: 49); small inputs get small buffers.  A piece
+  // never holds less than one index chunk (PCQ_INDEX_CHUNK_POINTS points, each column rounded up to 256 bytes), so a
+  // long record length (extra bytes) raises the floor.
   size_t chunk_bytes = 256u << 20;
-  if (const char* e = std::getenv("PCQ_CHUNK_MB")) {
-    chunk_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
+  const size_t chunk_floor = round_up((size_t)PCQ_INDEX_CHUNK_POINTS * max_per_point + 768 + 1024, 1u << 20);
+  const bool chunk_forced = std::getenv("PCQ_CHUNK_MB") != nullptr;
+  if (chunk_forced) {
+    chunk_bytes = (size_t)std::max(1, std::atoi(std::getenv("PCQ_CHUNK_MB"))) << 20;
   } else {
     size_t largest = 0;
     for (uint32_t i = 0; i < n_files; ++i) largest = std::max(largest, n_bytes[i]);
     chunk_bytes = std::min(chunk_bytes, std::max<size_t>(round_up(largest + 4096, 1u << 20), 4u << 20));
   }
+  chunk_bytes = std::max(chunk_bytes, chunk_floor);
   if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  if (std::getenv("PCQ_CHUNK_MB") ? ctx->chunk_cap != chunk_bytes : ctx->chunk_cap < chunk_bytes) {
+  if (chunk_forced ? ctx->chunk_cap != chunk_bytes : ctx->chunk_cap < chunk_bytes) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     for (int b = 0; b < kChunkBuffers; ++b) {
@@ -1624,9 +1590,14 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       ctx->chunk[b] = nullptr;
     }
     ctx->chunk_cap = 0;
-    for (int b = 0; b < kChunkBuffers; ++b) CU(cudaMalloc(&ctx->chunk[b], chunk_bytes + 1024));
+    for (int b = 0; b < kChunkBuffers; ++b)
+      if (cudaMalloc(&ctx->chunk[b], chunk_bytes + 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PCQ_ERR_NOMEM, "cannot allocate %zu bytes of HBM for the staging ring", chunk_bytes);
+      }
     ctx->chunk_cap = chunk_bytes;
   }
+  chunk_bytes = ctx->chunk_cap;  // (a larger ring left by an earlier call is used whole)
   for (int b = 0; b < kChunkBuffers; ++b) {
     if (!ctx->chunk_copied[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_copied[b], cudaEventDisableTiming));
     if (!ctx->chunk_free[b]) CU(cudaEventCreateWithFlags(&ctx->chunk_free[b], cudaEventDisableTiming));
@@ -1635,17 +1606,24 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
   std::vector<char> pageable(n_files, 0);
   bool any_pageable = false;
   for (uint32_t i = 0; i < n_files; ++i) {
-    pageable[i] = is_pinned_host(file_bytes[i]) ? 0 : 1;
+    // tested where this call's copies start: a rank of a sharded scan may have pinned only its own range of the image
+    const uint8_t* probe = static_cast<const uint8_t*>(file_bytes[i]);
+    if (ranges && fps[i].any && ranges[i].n_points != 0 && fps[i].layout == PCQ_LAYOUT_LAS)
+      probe += fps[i].d.point_data_off + std::min<uint64_t>(ranges[i].first_point, fps[i].d.n_points) * fps[i].d.record_len;
+    else if (ranges && (!fps[i].any || ranges[i].n_points == 0))
+      continue;
+    pageable[i] = is_pinned_host(probe) ? 0 : 1;
     any_pageable |= pageable[i] != 0;
   }
   if (std::getenv("PCQ_NO_BOUNCE")) any_pageable = false, std::fill(pageable.begin(), pageable.end(), 0);
   if (any_pageable) {
-    const size_t want = std::max(ctx->chunk_cap, chunk_bytes) + 1024;
+    const size_t want = chunk_bytes + 1024;
     if (ctx->bounce_cap < want) {
       CU(cudaStreamSynchronize(ctx->copy_stream));
       for (int b = 0; b < kChunkBuffers; ++b) {
         if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
         ctx->bounce[b] = nullptr;
+        ctx->bounce_busy[b] = false;
       }
       ctx->bounce_cap = 0;
       for (int b = 0; b < kChunkBuffers; ++b)
@@ -1677,72 +1655,73 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     if (hix->files.empty()) hix->files.resize(n_files);
     if (hix->files.size() != n_files)
       return fail(PCQ_ERR_ARG, "host index covers %zu files, this search names %u", hix->files.size(), n_files);
+    // chunk headers are only good for the image they were made from: an entry is keyed on the image's address,
+    // length and the header fields the filter depends on, and dropped when any of them changed
+    for (uint32_t i = 0; i < n_files; ++i) {
+      pcq_host_index::File& xf = hix->files[i];
+      const FilePlan& fp = fps[i];
+      uint64_t key = 1469598103934665603ull;
+      auto mixin = [&key](const void* p, size_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(p);
+        for (size_t k = 0; k < n; ++k) key = (key ^ b[k]) * 1099511628211ull;
+      };
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(file_bytes[i]);
+      mixin(&addr, sizeof(addr));
+      mixin(&n_bytes[i], sizeof(size_t));
+      mixin(&fp.d, sizeof(fp.d));
+      if (xf.n_chunks != 0 && xf.key != key) {  // another image sits at this position now
+        xf.has_box = xf.has_cls = false;
+        xf.unfetched = 0;
+        std::vector<pcq_chunk_header>().swap(xf.box);
+        std::vector<pcq_chunk_header>().swap(xf.cls);
+        if (xf.d_headers) {
+          CU(cudaStreamSynchronize(ctx->stream));
+          cudaFree(xf.d_headers);
+        }
+        xf.d_headers = nullptr;
+        xf.n_chunks = 0;
+      }
+      xf.key = key;
+    }
   }
 
-  struct Run {
-    uint64_t first, n;  // points
-  };
-  struct Piece {  // what one ring buffer holds: runs [run0, run0 + n_runs) of one file, packed back to back
-    uint32_t file;
-    uint32_t run0, n_runs;
-  };
-  struct FilePlan {
-    pcq_file_desc d;
-    uint8_t raw;
-    std::vector<SegmentPlan> plan;  // per query
-    std::vector<uint64_t> base;     // per query: scan index of the file's point 0 in its collector
-    uint32_t lane;
-    bool any, need_pos, need_cls, need_rgb;
-    bool build_box, build_cls;      // this pass computes that part of the file's chunk headers
-    double kept_fraction;           // points that cross PCIe / points of the file
-  };
-  std::vector<FilePlan> fps(n_files);
+  // Pass 2: scan bases, chunk-header use / build decisions, and the pieces that cross PCIe.
   std::vector<Run> runs;
   std::vector<Piece> pieces;
   std::vector<ChunkRun> cruns;
   pcq_scan_stats stats{};
   for (uint32_t i = 0; i < n_files; ++i) {
     FilePlan& fp = fps[i];
-    const int layout = layout_of_ext(exts[i]);
-    if (layout < 0) return fail(PCQ_ERR_FORMAT, "Unsupported file extension \"%s\"", exts[i] ? exts[i] : "");
-    RC(parse_header(file_bytes[i], n_bytes[i], layout, 1, &fp.d, &fp.raw));
-    if ((uint64_t)fp.d.point_data_off + fp.d.n_points * (uint64_t)fp.d.record_len > (uint64_t)n_bytes[i])
-      return fail(PCQ_ERR_IO, "file image %u is shorter than its header promises", i);
-    fp.lane = n_collectors == 1 ? 0 : i;
-    fp.plan.resize(n_queries);
-    fp.base.resize(n_queries);
-    fp.any = fp.need_pos = fp.need_cls = fp.need_rgb = false;
-    fp.build_box = fp.build_cls = false;
-    fp.kept_fraction = 1.0;
+    const int layout = fp.layout;
     for (uint32_t q = 0; q < n_queries; ++q) {
       pcq_collector* c = collectors[(size_t)q * n_collectors + fp.lane];
-      fp.base[q] = c->scan_total;
-      c->scan_total += fp.d.n_points;
-      RC(plan_file(fp.d, fp.raw, queries + q, &fp.plan[q]));
-      if (fp.plan[q].skip || fp.d.n_points == 0) {
-        fp.plan[q].skip = true;
-        continue;
+      if (ranges) {
+        fp.base[q] = ranges[i].scan_base;  // (a sharded scan: the caller knows where the file sits in the scan order)
+      } else {
+        fp.base[q] = c->scan_total;
+        c->scan_total += fp.d.n_points;
       }
-      const bool emit = c->kind != PCQ_COLLECT_COUNT;
-      fp.any = true;
-      fp.need_pos |= queries[q].kind == PCQ_QUERY_BOUNDS || emit;
-      fp.need_cls |= queries[q].kind == PCQ_QUERY_CLASS || emit;
-      fp.need_rgb |= emit && rgb_offset_in_record(fp.d.format) >= 0;
     }
     if (!fp.any) continue;
     const uint64_t N = fp.d.n_points;
-    stats.points_total += N;
+    // a sharded scan covers the point range [r_first, r_end) of the file only (group.cu)
+    uint64_t r_first = 0, r_end = N;
+    if (ranges) {
+      r_first = std::min<uint64_t>(ranges[i].first_point, N);
+      r_end = r_first + std::min<uint64_t>(ranges[i].n_points, N - r_first);
+      if (r_first % PCQ_INDEX_CHUNK_POINTS != 0)
+        return fail(PCQ_ERR_ARG, "point range of file %u starts at %llu: ranges start on multiples of %u points", i,
+                    (unsigned long long)r_first, PCQ_INDEX_CHUNK_POINTS);
+      if (hix) return fail(PCQ_ERR_ARG, "a host index cannot be combined with point ranges");
+      if (r_end == r_first) continue;
+    }
+    stats.points_total += r_end - r_first;
 
     // chunk headers of this file: use them when every query of the batch can be filtered, else build what the
     // columns of this pass allow ("while scanning first (without an index) ...", improvements.md:6)
     pcq_host_index::File* xf = hix ? &hix->files[i] : nullptr;
     bool filter = false;
     if (xf) {
-      if (xf->n_chunks != 0 && xf->n_points != N) {  // another file sits at this position now
-        xf->has_box = xf->has_cls = false;
-        if (xf->d_headers) cudaFree(xf->d_headers);
-        xf->d_headers = nullptr;
-      }
       xf->n_points = N;
       xf->n_chunks = (N + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS;
       filter = true;
@@ -1760,9 +1739,7 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       }
     }
 
-    uint64_t per_point = layout == PCQ_LAYOUT_LAS
-                             ? fp.d.record_len
-                             : (fp.need_pos ? 12 : 0) + (fp.need_cls ? 1 : 0) + (fp.need_rgb ? 6 : 0);
+    const uint64_t per_point = fp.per_point;
     // a run's columns are rounded up to 256 bytes each: three roundings per run at most
     uint64_t pts = (chunk_bytes - 1024 - 768) / per_point;
     pts = std::max<uint64_t>(PCQ_INDEX_CHUNK_POINTS, pts / PCQ_INDEX_CHUNK_POINTS * PCQ_INDEX_CHUNK_POINTS);
@@ -1789,12 +1766,12 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       for (const ChunkRun& r : cruns) kept += r.end - r.first;
       stats.chunks_skipped += xf->n_chunks - kept;
     } else {
-      cruns.push_back({0, (N + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS});
+      cruns.push_back({r_first / PCQ_INDEX_CHUNK_POINTS, (r_end + PCQ_INDEX_CHUNK_POINTS - 1) / PCQ_INDEX_CHUNK_POINTS});
     }
     uint64_t kept_points = 0;
     uint64_t room = 0;
     for (const ChunkRun& r : cruns) {
-      const uint64_t p0 = r.first * PCQ_INDEX_CHUNK_POINTS, p1 = std::min<uint64_t>(r.end * PCQ_INDEX_CHUNK_POINTS, N);
+      const uint64_t p0 = r.first * PCQ_INDEX_CHUNK_POINTS, p1 = std::min<uint64_t>(r.end * PCQ_INDEX_CHUNK_POINTS, r_end);
       for (uint64_t first = p0; first < p1; first += pts) {
         const uint64_t n = std::min<uint64_t>(pts, p1 - first);
         const uint64_t need = run_bytes(n);
@@ -1802,6 +1779,7 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
           pieces.push_back({i, (uint32_t)runs.size(), 0});
           room = chunk_bytes - 1024;
         }
+        if (need > room) return fail(PCQ_ERR_ARG, "internal: a run of %llu bytes does not fit a %zu-byte ring buffer", (unsigned long long)need, chunk_bytes);
         runs.push_back({first, n});
         pieces.back().n_runs++;
         room -= need;
@@ -1809,13 +1787,12 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
       }
     }
     stats.points_scanned += kept_points;
-    fp.kept_fraction = (double)kept_points / (double)N;
+    fp.kept_fraction = (double)kept_points / (double)(r_end - r_first);
   }
   struct Staged {
     const uint8_t *rec, *cls, *rgb;
   };
   std::vector<Staged> staged(runs.size());
-  bool bounce_used[kChunkBuffers] = {false, false, false};
   auto issue_copy = [&](size_t j) -> int {
     const Piece& pc = pieces[j];
     const FilePlan& fp = fps[pc.file];
@@ -1826,7 +1803,12 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     const uint64_t N = fp.d.n_points;
     const bool via_bounce = pageable[pc.file] != 0;
     uint8_t* hb = via_bounce ? static_cast<uint8_t*>(ctx->bounce[b]) : nullptr;
-    if (via_bounce && bounce_used[b]) CU(cudaEventSynchronize(ctx->bounce_done[b]));  // the slot's last H2D has left it
+    // the slot's last H2D (possibly issued by an EARLIER call on this context: COUNT searches return without
+    // synchronising) must have left it before host threads overwrite it
+    if (via_bounce && ctx->bounce_busy[b]) {
+      CU(cudaEventSynchronize(ctx->bounce_done[b]));
+      ctx->bounce_busy[b] = false;
+    }
     // one column (or the record block): host bytes -> [pinned bounce slot ->] device chunk at offset o
     auto put = [&](size_t o, const uint8_t* from, size_t n) -> int {
       if (via_bounce) {
@@ -1868,12 +1850,15 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     }
     if (via_bounce) {
       CU(cudaEventRecord(ctx->bounce_done[b], ctx->copy_stream));
-      bounce_used[b] = true;
+      ctx->bounce_busy[b] = true;
     }
     CU(cudaEventRecord(ctx->chunk_copied[b], ctx->copy_stream));
     return PCQ_OK;
   };
 
+  // An error inside the streaming loop must not leave H2D copies queued against the caller's buffers and the bounce
+  // slots: the loop runs in a lambda and every exit drains both streams first.
+  auto stream_all = [&]() -> int {
   // buffers start out free
   for (int b = 0; b < kChunkBuffers; ++b) CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   const size_t prefetch = kChunkBuffers - 1;
@@ -1925,6 +1910,15 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
     }
     CU(cudaEventRecord(ctx->chunk_free[b], ctx->stream));
   }
+  return PCQ_OK;
+  };
+  const int stream_rc = stream_all();
+  if (stream_rc != PCQ_OK) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < kChunkBuffers; ++b) ctx->bounce_busy[b] = false;
+    return stream_rc;
+  }
   if (hix) {
     for (uint32_t i = 0; i < n_files; ++i) {
       pcq_host_index::File& xf = hix->files[i];
@@ -1936,19 +1930,21 @@ static int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const 
   ctx->stats = stats;
   return PCQ_OK;
 }
+}  // namespace pcq
+extern "C" {
 
 int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
                           uint32_t n_files, const pcq_query* query, pcq_collector* const* collectors,
                           uint32_t n_collectors) {
   if (!query) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
-  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, query, 1, collectors, n_collectors, nullptr);
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, query, 1, collectors, n_collectors, nullptr, nullptr);
 }
 
 int pcq_search_host_files_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
                                 const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
                                 pcq_collector* const* collectors, uint32_t n_collectors_per_query) {
   if (!queries && n_queries) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
-  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, nullptr);
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, nullptr, nullptr);
 }
 
 int pcq_host_index_create(pcq_ctx* ctx, pcq_host_index** out) {
@@ -1985,7 +1981,7 @@ int pcq_search_host_files_indexed(pcq_ctx* ctx, const void* const* file_bytes, c
                                   pcq_collector* const* collectors, uint32_t n_collectors_per_query, pcq_host_index* index) {
   if (!queries && n_queries) return fail(PCQ_ERR_ARG, "pcq_search: null argument");
   if (!index) return fail(PCQ_ERR_ARG, "null index");
-  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, index);
+  return search_host_multi(ctx, file_bytes, n_bytes, exts, n_files, queries, n_queries, collectors, n_collectors_per_query, index, nullptr);
 }
 
 // ---- multi-GPU density exchange --------------------------------------------------------------------
@@ -2013,6 +2009,8 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
   }
   CU(cudaMemsetAsync(ctx->part_scratch, 0, 2ull * n_parts * sizeof(unsigned long long), ctx->stream));
   GridDev g = grid_view(c);
+  g.own_parts = 0;                // every locally occupied cell is exported
+  c->table_holds_winners = true;  // until phase 3 below has put the distances back
   for (int phase = 0; phase < 3; ++phase)
     if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");
   if (launch_grid_emit(g, n, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
@@ -2041,6 +2039,7 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
                        ctx->sm_count, ctx->stream) != 0)
     return fail(PCQ_ERR_CUDA, "launch failed");
   if (launch_grid_final_phase(g, n, 3, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");  // distances back
+  c->table_holds_winners = false;
   ctx->launches += 2;
   CU(cudaStreamSynchronize(ctx->stream));
   *out_dev_candidates = c->d_export;

@@ -1918,7 +1918,8 @@ __global__ void k_grid_final_phase(GridDev g, uint64_t n, int phase) {
     if (c.scan_idx == kCandEmpty) continue;
     if (phase == 0) {
       bool fin = false;
-      if (alias_find(g, c.key) == ~0u) {  // affected keys come from the replay
+      const bool mine = g.own_parts <= 1u || (uint32_t)(mix64(c.key) % g.own_parts) == g.own_me;  // multi-GPU: owner only
+      if (mine && alias_find(g, c.key) == ~0u) {  // affected keys come from the replay
         const uint64_t slot = grid_slot(g, c.key, false);
         fin = slot != ~0ull && g.table[slot] == c.dist_bits;
       }

@@ -77,6 +77,8 @@ struct GridDev {
   const uint32_t* alias_ord;
   uint64_t alias_slots;  // power of two, 0 when no key is affected yet
   uint32_t log_only;     // 1: second pass of a launch that met new affected keys — log their points, insert nothing
+  uint32_t own_parts;    // finalisation: > 1 = only cells with mix64(key) % own_parts == own_me are finalists (multi-GPU owner)
+  uint32_t own_me;
   uint32_t pad_;
   Candidate* log;        // replay log: {key, -, scan index, point} of every point of an affected key / aliased point
   unsigned long long* log_count;

@@ -9,8 +9,30 @@
 #include <climits>
 #include <cstring>
 
+#include <cstdarg>
+#include <cstdio>
+
 #include "../../include/pcq_synth.h"
-#include "host_logic.hpp"
+
+// libpcq_synth.so is self-contained (it does not link libpcq.so): the CPU reference arm of bench.py generates its
+// inputs with it without mapping the product library.
+namespace pcq {
+namespace {
+thread_local char g_synth_err[512] = "";
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(g_synth_err, sizeof(g_synth_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+uint16_t format_record_len(uint8_t fmt) {  // ASPRS LAS 1.x point data record formats 0..3
+  static const uint16_t len[4] = {20, 28, 26, 34};
+  return fmt < 4 ? len[fmt] : 0xFFFF;
+}
+}  // namespace
+}  // namespace pcq
 
 #define HD __host__ __device__ __forceinline__
 
@@ -154,7 +176,8 @@ HD int record_fields(uint8_t format, int record_len, FieldDef* out) {
   return n;
 }
 
-HD void store_record(const pcq_synth_spec& sp, uint64_t i, const uint8_t* rec, uint8_t* dst) {
+// `i` = index of the record inside the block at dst, `n_col` = points per LAST column of that block
+HD void store_record(const pcq_synth_spec& sp, uint64_t i, uint64_t n_col, const uint8_t* rec, uint8_t* dst) {
   if (sp.layout == PCQ_LAYOUT_LAS) {
     uint8_t* p = dst + i * (uint64_t)sp.record_len;
     for (int b = 0; b < sp.record_len; ++b) p[b] = rec[b];
@@ -163,19 +186,19 @@ HD void store_record(const pcq_synth_spec& sp, uint64_t i, const uint8_t* rec, u
   FieldDef fd[12];
   const int nf = record_fields(sp.format, sp.record_len, fd);
   for (int k = 0; k < nf; ++k) {
-    uint8_t* p = dst + (uint64_t)fd[k].off * sp.n_points + i * (uint64_t)fd[k].size;
+    uint8_t* p = dst + (uint64_t)fd[k].off * n_col + i * (uint64_t)fd[k].size;
     for (int b = 0; b < fd[k].size; ++b) p[b] = rec[fd[k].off + b];
   }
 }
 
-__global__ void k_synth(pcq_synth_spec sp, uint8_t* dst, int* minmax) {
+__global__ void k_synth(pcq_synth_spec sp, uint64_t first, uint64_t n, uint8_t* dst, int* minmax) {
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sp.n_points; i += stride) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint8_t rec[kMaxRecord];
     Fields f;
-    make_record(sp, i, rec, &f);
-    store_record(sp, i, rec, dst);
+    make_record(sp, first + i, rec, &f);
+    store_record(sp, i, n, rec, dst);
     mn[0] = min(mn[0], f.x);
     mn[1] = min(mn[1], f.y);
     mn[2] = min(mn[2], f.z);
@@ -271,50 +294,72 @@ int pcq_synth_desc(const pcq_synth_spec* sp, const int32_t minmax[6], pcq_file_d
   return PCQ_OK;
 }
 
-int pcq_synth_host(const pcq_synth_spec* sp, void* out, size_t cap) {
+int pcq_synth_host_points(const pcq_synth_spec* sp, uint64_t first_point, uint64_t n_points, void* out_points,
+                          int32_t minmax[6]) {
   int rc = check_spec(sp);
   if (rc != PCQ_OK) return rc;
-  if (!out || cap < pcq_synth_file_size(sp)) return pcq::fail(PCQ_ERR_ARG, "output buffer too small");
-  uint8_t* base = static_cast<uint8_t*>(out) + 227;
+  if (!minmax || (!out_points && n_points)) return pcq::fail(PCQ_ERR_ARG, "null argument");
+  if (first_point > sp->n_points || n_points > sp->n_points - first_point) return pcq::fail(PCQ_ERR_ARG, "point range outside the file");
+  uint8_t* base = static_cast<uint8_t*>(out_points);
   int32_t mm[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-  for (uint64_t i = 0; i < sp->n_points; ++i) {
+  for (uint64_t i = 0; i < n_points; ++i) {
     uint8_t rec[kMaxRecord];
     Fields f;
-    make_record(*sp, i, rec, &f);
-    store_record(*sp, i, rec, base);
+    make_record(*sp, first_point + i, rec, &f);
+    store_record(*sp, i, n_points, rec, base);
     const int32_t v[3] = {f.x, f.y, f.z};
     for (int a = 0; a < 3; ++a) {
       if (v[a] < mm[a]) mm[a] = v[a];
       if (v[a] > mm[3 + a]) mm[3 + a] = v[a];
     }
   }
+  for (int a = 0; a < 6; ++a) minmax[a] = mm[a];
+  return PCQ_OK;
+}
+
+int pcq_synth_host(const pcq_synth_spec* sp, void* out, size_t cap) {
+  int rc = check_spec(sp);
+  if (rc != PCQ_OK) return rc;
+  if (!out || cap < pcq_synth_file_size(sp)) return pcq::fail(PCQ_ERR_ARG, "output buffer too small");
+  int32_t mm[6];
+  rc = pcq_synth_host_points(sp, 0, sp->n_points, static_cast<uint8_t*>(out) + 227, mm);
+  if (rc != PCQ_OK) return rc;
   if (sp->n_points == 0)
     for (int a = 0; a < 6; ++a) mm[a] = 0;
   return pcq_synth_header(sp, mm, out);
 }
 
-int pcq_synth_device(pcq_ctx* ctx, const pcq_synth_spec* sp, void* dev_point_data, int32_t minmax[6]) {
+int pcq_synth_device_points(int device, const pcq_synth_spec* sp, uint64_t first_point, uint64_t n_points,
+                            void* dev_point_data, int32_t minmax[6]) {
   int rc = check_spec(sp);
   if (rc != PCQ_OK) return rc;
-  if (!ctx || !minmax || (!dev_point_data && sp->n_points)) return pcq::fail(PCQ_ERR_ARG, "null argument");
-  rc = pcq_ctx_synchronize(ctx);  // also selects the context's device
-  if (rc != PCQ_OK) return rc;
+  if (!minmax || (!dev_point_data && n_points)) return pcq::fail(PCQ_ERR_ARG, "null argument");
+  if (first_point > sp->n_points || n_points > sp->n_points - first_point) return pcq::fail(PCQ_ERR_ARG, "point range outside the file");
+  if (cudaSetDevice(device) != cudaSuccess) return pcq::fail(PCQ_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(cudaGetLastError()));
   int* d_mm = nullptr;
   if (cudaMalloc(&d_mm, 6 * sizeof(int)) != cudaSuccess) return pcq::fail(PCQ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
   int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
   cudaMemcpy(d_mm, init, sizeof(init), cudaMemcpyHostToDevice);
-  if (sp->n_points) {
-    uint64_t blocks = (sp->n_points + 255) / 256;
+  if (n_points) {
+    uint64_t blocks = (n_points + 255) / 256;
     if (blocks > 148ull * 16) blocks = 148ull * 16;
-    k_synth<<<(unsigned)blocks, 256>>>(*sp, static_cast<uint8_t*>(dev_point_data), d_mm);
+    k_synth<<<(unsigned)blocks, 256>>>(*sp, first_point, n_points, static_cast<uint8_t*>(dev_point_data), d_mm);
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(minmax, d_mm, sizeof(init), cudaMemcpyDeviceToHost);
   cudaFree(d_mm);
   if (e != cudaSuccess) return pcq::fail(PCQ_ERR_CUDA, "synthetic data kernel failed: %s", cudaGetErrorString(e));
-  if (sp->n_points == 0)
-    for (int a = 0; a < 6; ++a) minmax[a] = 0;
   return PCQ_OK;
 }
+
+int pcq_synth_device(int device, const pcq_synth_spec* sp, void* dev_point_data, int32_t minmax[6]) {
+  if (!sp) return pcq::fail(PCQ_ERR_ARG, "null spec");
+  const int rc = pcq_synth_device_points(device, sp, 0, sp->n_points, dev_point_data, minmax);
+  if (rc == PCQ_OK && sp->n_points == 0)
+    for (int a = 0; a < 6; ++a) minmax[a] = 0;
+  return rc;
+}
+
+const char* pcq_synth_last_error(void) { return pcq::g_synth_err; }
 
 }  // extern "C"

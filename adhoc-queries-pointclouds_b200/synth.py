@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import binding as B
-from .binding import check, lib
+from .binding import check_synth as check, synth_lib as lib
 
 FORMAT_LEN = {0: 20, 1: 28, 2: 26, 3: 34}
 
@@ -73,10 +73,35 @@ def host_file(spec: B.SynthSpec) -> np.ndarray:
 def device_points(ctx, spec: B.SynthSpec, dev_ptr: int):
     """Fill device memory with the point data of `spec`; -> (raw minmax[6], FileDesc)."""
     mm = (C.c_int32 * 6)()
-    check(lib.pcq_synth_device(ctx.handle, C.byref(spec), C.c_void_p(int(dev_ptr)), mm))
+    ctx.synchronize()
+    check(lib.pcq_synth_device(int(ctx.device), C.byref(spec), C.c_void_p(int(dev_ptr)), mm))
     desc = B.FileDesc()
     check(lib.pcq_synth_desc(C.byref(spec), mm, C.byref(desc)))
     return [int(v) for v in mm], desc
+
+
+def device_point_range(device: int, spec: B.SynthSpec, first_point: int, n_points: int, dev_ptr: int):
+    """Point data of the range [first_point, first_point + n_points) of the file into device memory (a block of its
+    own); -> raw minmax[6] of the range (INT_MAX / INT_MIN when it is empty)."""
+    mm = (C.c_int32 * 6)()
+    check(lib.pcq_synth_device_points(int(device), C.byref(spec), int(first_point), int(n_points), C.c_void_p(int(dev_ptr)), mm))
+    return [int(v) for v in mm]
+
+
+def host_point_range(spec: B.SynthSpec, first_point: int, n_points: int, out: np.ndarray):
+    """Same bytes on the host, written into `out` (uint8, C-contiguous); -> raw minmax[6] of the range.  Releases the
+    GIL: callers split files over threads."""
+    assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
+    mm = (C.c_int32 * 6)()
+    check(lib.pcq_synth_host_points(C.byref(spec), int(first_point), int(n_points), C.c_void_p(out.ctypes.data), mm))
+    return [int(v) for v in mm]
+
+
+def desc_of(spec: B.SynthSpec, minmax: Sequence[int]) -> B.FileDesc:
+    mm = (C.c_int32 * 6)(*[int(v) for v in minmax])
+    desc = B.FileDesc()
+    check(lib.pcq_synth_desc(C.byref(spec), mm, C.byref(desc)))
+    return desc
 
 
 def header_bytes(spec: B.SynthSpec, minmax: Sequence[int]) -> np.ndarray:

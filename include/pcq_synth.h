@@ -41,15 +41,27 @@ typedef struct pcq_synth_spec {
   uint16_t class_cum[8]; /* cumulative thresholds out of 65536; class k if r16 < class_cum[k] (last must be 65535) */
 } pcq_synth_spec;
 
+/* libpcq_synth.so is self-contained (no dependency on libpcq.so); errors: PCQ_OK or a negative pcq_status,
+ * message through pcq_synth_last_error(). */
+const char* pcq_synth_last_error(void);
+
 /* size of the whole file image (227-byte LAS 1.2 header + point data) */
 size_t pcq_synth_file_size(const pcq_synth_spec* spec);
 
 /* Writes the whole file image (header with true min/max + points) into host memory. */
 int pcq_synth_host(const pcq_synth_spec* spec, void* out, size_t cap);
 
-/* Writes the same point data (no header) into device memory with a kernel; returns the raw
- * coordinate minima / maxima in minmax[0..2] / minmax[3..5]. */
-int pcq_synth_device(pcq_ctx* ctx, const pcq_synth_spec* spec, void* dev_point_data, int32_t minmax[6]);
+/* Point data of the range [first_point, first_point + n_points) of the file (no header) into host memory, as a block
+ * of its own (LAS: n_points records; LAST: columns of n_points entries each); raw coordinate minima / maxima of the
+ * range in minmax[0..2] / minmax[3..5].  Thread-safe: callers split a file over threads. */
+int pcq_synth_host_points(const pcq_synth_spec* spec, uint64_t first_point, uint64_t n_points, void* out_points,
+                          int32_t minmax[6]);
+
+/* The same bytes written into device memory by a kernel on `device` (synchronous). */
+int pcq_synth_device_points(int device, const pcq_synth_spec* spec, uint64_t first_point, uint64_t n_points,
+                            void* dev_point_data, int32_t minmax[6]);
+/* whole file: first_point = 0, n_points = spec->n_points */
+int pcq_synth_device(int device, const pcq_synth_spec* spec, void* dev_point_data, int32_t minmax[6]);
 
 /* 227-byte LAS 1.2 header for `spec` whose bounds are minmax * scale + offset. */
 int pcq_synth_header(const pcq_synth_spec* spec, const int32_t minmax[6], void* out227);
