@@ -6,7 +6,8 @@ root).  The product is ``libpcq.so`` (csrc/: hand-written sm_100a CUDA kernels b
 include/pcq.h) plus the `query` CLI; this package is the Python twin of the reference's
 Searcher / ResultCollector interface that the tests and bench.py drive it through.
 """
-from . import binding, sharding, synth  # noqa: F401
+from . import binding, group, sharding, synth  # noqa: F401
+from .group import Dataset, Group, Result, shard_plan  # noqa: F401
 from .binding import (  # noqa: F401
     CANDIDATE_DTYPE,
     POINT_DTYPE,

@@ -86,6 +86,11 @@ class SynthSpec(C.Structure):
 
 
 INDEX_CHUNK_POINTS = 8192
+SHARD_RANGES, SHARD_FILES = 0, 1
+GROUP_ID_BYTES = 128
+
+SHARD_DTYPE = np.dtype([("file", "<u4"), ("rank", "<u4"), ("first_point", "<u8"), ("n_points", "<u8")])
+assert SHARD_DTYPE.itemsize == 24
 
 # pcq_chunk_header: integer AABB of the raw x/y/z fields + set of class bytes of one chunk (64 bytes)
 CHUNK_HEADER_DTYPE = np.dtype(
@@ -162,6 +167,29 @@ def _load() -> C.CDLL:
         "pcq_host_free": (None, [vp]),
         "pcq_grid_export_candidates": (C.c_int, [vp, u32, P(vp), P(u64)]),
         "pcq_grid_import_candidates": (C.c_int, [vp, vp, u64]),
+        "pcq_host_register": (C.c_int, [vp, sz]),
+        "pcq_host_unregister": (C.c_int, [vp]),
+        "pcq_ctx_bind_host_thread": (C.c_int, [vp, P(C.c_int)]),
+        "pcq_group_create": (C.c_int, [P(C.c_int), u32, P(vp)]),
+        "pcq_group_unique_id": (C.c_int, [vp]),
+        "pcq_group_create_rank": (C.c_int, [C.c_int, u32, u32, vp, P(vp)]),
+        "pcq_group_destroy": (None, [vp]),
+        "pcq_group_world": (u32, [vp]),
+        "pcq_group_local_count": (u32, [vp]),
+        "pcq_group_local_rank": (u32, [vp, u32]),
+        "pcq_group_ctx": (vp, [vp, u32]),
+        "pcq_group_launch_count": (u64, [vp]),
+        "pcq_group_synchronize": (C.c_int, [vp]),
+        "pcq_shard_plan": (C.c_int, [P(u64), u32, u32, C.c_int, vp, u64, P(u64)]),
+        "pcq_group_stage_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, C.c_int, P(vp)]),
+        "pcq_group_wrap_files": (C.c_int, [vp, P(u64), u32, P(vp), P(u32), P(u32), u32, P(vp)]),
+        "pcq_dataset_release": (None, [vp]),
+        "pcq_group_search": (C.c_int, [vp, vp, P(Query), u32, C.c_int, vp, vp, C.c_double, C.c_int, P(vp)]),
+        "pcq_group_search_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), u32, C.c_int, vp, vp,
+                                                  C.c_double, C.c_int, C.c_int, P(vp)]),
+        "pcq_result_counts": (C.c_int, [vp, P(P(u64)), P(u32)]),
+        "pcq_result_points": (C.c_int, [vp, u32, P(vp), P(u64)]),
+        "pcq_result_release": (None, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == an exported symbol is missing

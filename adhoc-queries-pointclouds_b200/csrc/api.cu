@@ -6,8 +6,16 @@
 // launch ONE kernel for the whole batch.  All per-point work is in kernels.cu; there is no CPU scan.
 #include <cuda_runtime.h>
 
+#ifdef __linux__
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
+
 #include <algorithm>
+#include <cctype>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -253,7 +261,7 @@ GridDev grid_view(const pcq_collector* c) {
   g.alias_keys = c->a_slots ? c->d_akeys : nullptr;
   g.alias_ord = c->a_slots ? c->d_aord : nullptr;
   g.alias_slots = c->a_slots;
-  g.log_only = c->log_only_mode ? 1u : 0u;
+  g.log_only = c->pass_mode == 1 ? 1u : 0u;
   g.own_parts = c->own_parts;
   g.own_me = c->own_me;
   g.log = c->d_log;
@@ -805,31 +813,33 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
       continue;
     }
     bool any_logged = false;
-    for (uint32_t l = 0; l < n_collectors; ++l) any_logged |= blocks[l].log_count != 0;
-    if (collectors[0]->log_only_mode) {
-      // group-wide ordered replay (group.cu): this pass only collects the points of the affected keys; the launch's
-      // log is appended to the collector's raw log, nothing is inserted or folded here
-      for (uint32_t l = 0; l < n_collectors; ++l) {
-        pcq_collector* c = collectors[l];
-        const uint64_t n_log = blocks[l].log_count;
-        if (n_log == 0) continue;
-        if (c->rawlog_cap < c->rawlog_len + n_log) {
-          const uint64_t cap = std::max<uint64_t>((c->rawlog_len + n_log) * 2, 1u << 14);
-          Candidate* nb = nullptr;
-          if (cudaMalloc(&nb, cap * sizeof(Candidate)) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(PCQ_ERR_NOMEM, "cannot allocate a raw replay log of %llu entries", (unsigned long long)cap);
-          }
-          if (c->rawlog_len) CU(cudaMemcpyAsync(nb, c->d_rawlog, c->rawlog_len * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
-          CU(cudaStreamSynchronize(ctx->stream));
-          if (c->d_rawlog) cudaFree(c->d_rawlog);
-          c->d_rawlog = nb;
-          c->rawlog_cap = cap;
-        }
-        CU(cudaMemcpyAsync(c->d_rawlog + c->rawlog_len, c->d_log, n_log * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
-        c->rawlog_len += n_log;
+    // group-wide ordered replay (group.cu): a log-only pass only collects the points of the affected keys; the
+    // launch's log is appended to the collector's raw log, nothing is inserted or folded here
+    any_logged = false;
+    for (uint32_t l = 0; l < n_collectors; ++l) {
+      pcq_collector* c = collectors[l];
+      const uint64_t n_log = blocks[l].log_count;
+      if (c->pass_mode != 1) {
+        any_logged |= n_log != 0;
+        continue;
       }
-      any_logged = false;
+      if (n_log == 0) continue;
+      if (c->rawlog_cap < c->rawlog_len + n_log) {
+        const uint64_t cap = std::max<uint64_t>((c->rawlog_len + n_log) * 2, 1u << 14);
+        Candidate* nb = nullptr;
+        if (cudaMalloc(&nb, cap * sizeof(Candidate)) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(PCQ_ERR_NOMEM, "cannot allocate a raw replay log of %llu entries", (unsigned long long)cap);
+        }
+        if (c->rawlog_len) CU(cudaMemcpyAsync(nb, c->d_rawlog, c->rawlog_len * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (c->d_rawlog) cudaFree(c->d_rawlog);
+        c->d_rawlog = nb;
+        c->rawlog_cap = cap;
+      }
+      CU(cudaMemcpyAsync(c->d_rawlog + c->rawlog_len, c->d_log, n_log * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
+      c->rawlog_len += n_log;
+      blocks[l].log_count = 0;
     }
     if (any_logged) RC(alias_slow_path(ctx, segs, P, variant, R, min_align, collectors, n_collectors, blocks, epoch0, lane_lo));
     for (uint32_t l = 0; l < n_collectors; ++l) {
@@ -1252,7 +1262,7 @@ int pcq_collector_reset(pcq_collector* c) {
   c->astates.clear();
   c->a_slots = 0;
   c->scan_hi = 0;
-  c->log_only_mode = false;
+  c->pass_mode = 0;
   c->rawlog_len = 0;
   c->own_parts = c->own_me = 0;
   if (c->kind == PCQ_COLLECT_GRID) {
@@ -1423,7 +1433,7 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     if (!f->has_scan_base) c->scan_total += f->n_points;
     SegmentPlan plan;
     RC(plan_file(f->desc, f->raw_format, query, &plan));
-    if (plan.skip || f->n_points == 0) continue;
+    if (plan.skip || f->n_points == 0 || c->pass_mode == 2) continue;
     if (ctx->auto_index_after != 0 && f->index.empty() && f->scans >= ctx->auto_index_after) RC(pcq_file_build_index(f));
     f->scans++;
     st.points_total += f->n_points;
@@ -1494,6 +1504,82 @@ void pcq_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+int pcq_host_register(void* p, size_t n_bytes) {
+  if (!p || !n_bytes) return fail(PCQ_ERR_ARG, "pcq_host_register: null argument");
+  const cudaError_t e = cudaHostRegister(p, n_bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes of host memory: %s", n_bytes, cudaGetErrorString(e));
+  }
+  return PCQ_OK;
+}
+
+int pcq_host_unregister(void* p) {
+  if (!p) return PCQ_OK;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PCQ_ERR_ARG, "pcq_host_unregister: not a registered range");
+  }
+  return PCQ_OK;
+}
+
+int pcq_ctx_bind_host_thread(pcq_ctx* ctx, int* out_node) {
+  if (!ctx) return fail(PCQ_ERR_ARG, "null context");
+  if (out_node) *out_node = -1;
+#ifdef __linux__
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->device) != cudaSuccess) {
+    cudaGetLastError();
+    return PCQ_OK;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+  char path[128];
+  std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  int node = -1;
+  if (FILE* f = std::fopen(path, "r")) {
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+  }
+  if (node < 0) return PCQ_OK;  // single-node box or a platform that does not say
+  std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n_cpus = 0;
+  if (FILE* f = std::fopen(path, "r")) {
+    int a = 0, b = 0;
+    for (;;) {
+      if (std::fscanf(f, "%d", &a) != 1) break;
+      b = a;
+      int ch = std::fgetc(f);
+      if (ch == '-') {
+        if (std::fscanf(f, "%d", &b) != 1) b = a;
+        ch = std::fgetc(f);
+      }
+      for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+        CPU_SET(c, &set);
+        ++n_cpus;
+      }
+      if (ch != ',') break;
+    }
+    std::fclose(f);
+  }
+  // only CPUs this process may use anyway (a container's cpuset)
+  cpu_set_t allowed;
+  if (n_cpus && sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+    cpu_set_t both;
+    CPU_AND(&both, &set, &allowed);
+    if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof(both), &both);
+  }
+  // first-touch placement follows the thread; ask for the node explicitly as well (MPOL_PREFERRED = 1)
+  if (node < 64) {
+    unsigned long mask = 1ul << node;
+    syscall(SYS_set_mempolicy, 1, &mask, (unsigned long)(8 * sizeof(mask)));
+  }
+  if (out_node) *out_node = node;
+#endif
+  return PCQ_OK;
+}
+
 // Host-staged scan: file images stream through a ring of HBM chunk buffers; the copy of chunk k+2
 // overlaps the scan of chunk k.  Replaces mmap + page-fault driven reads (las.rs:24-31).  Several
 // queries can share one pass: every chunk is scanned by each query that needs its file while it is
@@ -1551,7 +1637,7 @@ int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t*
     for (uint32_t q = 0; q < n_queries; ++q) {
       const pcq_collector* c = collectors[(size_t)q * n_collectors + fp.lane];
       RC(plan_file(fp.d, fp.raw, queries + q, &fp.plan[q]));
-      if (fp.plan[q].skip || fp.d.n_points == 0) {
+      if (fp.plan[q].skip || fp.d.n_points == 0 || c->pass_mode == 2 || (ranges && ranges[i].n_points == 0)) {
         fp.plan[q].skip = true;
         continue;
       }

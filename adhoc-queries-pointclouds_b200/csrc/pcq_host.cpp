@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 
 namespace pcq_host {
 
@@ -128,36 +129,78 @@ void Searcher::search_file(const std::string& path, SearchImplementation impl, R
   search_files({path}, impl, {&collector});
 }
 
-void Searcher::search_files(const std::vector<std::string>& paths, SearchImplementation impl,
-                            const std::vector<ResultCollector*>& collectors) {
-  if (impl != SearchImplementation::Optimized)
-    throw Error(PCQ_ERR_ARG,
-                "SearchImplementation::Regular (pasture readers + f64 AABB::contains) is not part of the accelerated path; "
-                "pass --optimized or use the reference");
+namespace {
+
+// the inputs of one search: mapped like the reference maps them (las.rs:24-31), extensions checked as searcher.rs:50-90
+struct MappedInputs {
   std::vector<std::unique_ptr<MappedFile>> maps;
   std::vector<const void*> ptrs;
   std::vector<size_t> sizes;
   std::vector<std::string> exts;
-  for (const std::string& p : paths) {
-    maps.emplace_back(new MappedFile(p));
-    std::string ext = maps.back()->extension();
-    // searcher.rs:50-90: las / laz / last / lazer; everything else is an error
-    if (ext.empty()) throw Error(PCQ_ERR_FORMAT, "Invalid extension on file " + p);
-    if (ext == "laz" || ext == "lazer")
-      throw Error(PCQ_ERR_FORMAT, "file " + p + ": LAZ / LAZER decoding is out of scope of the accelerated path and stays on the reference");
-    if (ext != "las" && ext != "last") throw Error(PCQ_ERR_FORMAT, "Unsupported file extension in file " + p);
-    ptrs.push_back(maps.back()->data());
-    sizes.push_back(maps.back()->size());
-    exts.push_back(ext);
-  }
   std::vector<const char*> ext_c;
-  for (const std::string& e : exts) ext_c.push_back(e.c_str());
+  explicit MappedInputs(const std::vector<std::string>& paths) {
+    for (const std::string& p : paths) {
+      maps.emplace_back(new MappedFile(p));
+      std::string ext = maps.back()->extension();
+      if (ext.empty()) throw Error(PCQ_ERR_FORMAT, "Invalid extension on file " + p);
+      if (ext == "laz" || ext == "lazer")
+        throw Error(PCQ_ERR_FORMAT, "file " + p + ": LAZ / LAZER decoding is out of scope of the accelerated path and stays on the reference");
+      if (ext != "las" && ext != "last") throw Error(PCQ_ERR_FORMAT, "Unsupported file extension in file " + p);
+      ptrs.push_back(maps.back()->data());
+      sizes.push_back(maps.back()->size());
+      exts.push_back(ext);
+    }
+    for (const std::string& e : exts) ext_c.push_back(e.c_str());
+  }
+};
+
+void require_optimized(SearchImplementation impl) {
+  if (impl != SearchImplementation::Optimized)
+    throw Error(PCQ_ERR_ARG,
+                "SearchImplementation::Regular (pasture readers + f64 AABB::contains) is not part of the accelerated path; "
+                "pass --optimized or use the reference");
+}
+
+}  // namespace
+
+void Searcher::search_files(const std::vector<std::string>& paths, SearchImplementation impl,
+                            const std::vector<ResultCollector*>& collectors) {
+  require_optimized(impl);
+  if (!ctx_) throw Error(PCQ_ERR_ARG, "this searcher has no device context (it was made for a Group search)");
+  MappedInputs in(paths);
   std::vector<pcq_collector*> ch;
   for (ResultCollector* c : collectors) ch.push_back(c->handle());
   pcq_query q = query();
-  check(pcq_search_host_files(ctx_.get(), ptrs.data(), sizes.data(), ext_c.data(), (uint32_t)paths.size(), &q, ch.data(),
+  check(pcq_search_host_files(ctx_->get(), in.ptrs.data(), in.sizes.data(), in.ext_c.data(), (uint32_t)paths.size(), &q, ch.data(),
                               (uint32_t)ch.size()));
-  check(pcq_ctx_synchronize(ctx_.get()));  // the mappings go away when we return
+  check(pcq_ctx_synchronize(ctx_->get()));  // the mappings go away when we return
+}
+
+Group::Group(uint32_t n_gpus) { check(pcq_group_create(nullptr, n_gpus, &g_)); }
+Group::~Group() { pcq_group_destroy(g_); }
+
+GroupResult::~GroupResult() { pcq_result_release(r_); }
+std::vector<uint64_t> GroupResult::counts() const {
+  const uint64_t* c = nullptr;
+  uint32_t n = 0;
+  check(pcq_result_counts(r_, &c, &n));
+  return std::vector<uint64_t>(c, c + n);
+}
+bool GroupResult::points(uint32_t lane, const pcq_point** out, uint64_t* n) const {
+  check(pcq_result_points(r_, lane, out, n));
+  return *out != nullptr || *n == 0;
+}
+
+GroupResult search_files_on_group(Group& group, const std::vector<std::string>& paths, SearchImplementation impl,
+                                  const Searcher& searcher, int kind, const AABB* grid_bounds, double cell_size, bool per_file) {
+  require_optimized(impl);
+  MappedInputs in(paths);
+  const pcq_query q = searcher.to_query();
+  pcq_result* r = nullptr;
+  check(pcq_group_search_host_files(group.get(), in.ptrs.data(), in.sizes.data(), in.ext_c.data(), (uint32_t)paths.size(), &q, 1, kind,
+                                    grid_bounds ? grid_bounds->min : nullptr, grid_bounds ? grid_bounds->max : nullptr, cell_size,
+                                    per_file ? 1 : 0, PCQ_SHARD_RANGES, &r));
+  return GroupResult(r);
 }
 
 pcq_query BoundsSearcher::query() const {

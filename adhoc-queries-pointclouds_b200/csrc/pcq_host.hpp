@@ -109,21 +109,25 @@ class MappedFile {
 // trait Searcher (searcher.rs:24-31)
 class Searcher {
  public:
-  explicit Searcher(Context& ctx) : ctx_(ctx) {}
+  explicit Searcher(Context& ctx) : ctx_(&ctx) {}
+  Searcher() = default;  // predicate only: searched through a Group (search_files_on_group)
   virtual ~Searcher() = default;
   void search_file(const std::string& path, SearchImplementation impl, ResultCollector& collector);
   // one batch: collectors.size() == 1 (sequential) or == paths.size() (parallel)
   void search_files(const std::vector<std::string>& paths, SearchImplementation impl,
                     const std::vector<ResultCollector*>& collectors);
+  // the predicate as the C ABI takes it
+  pcq_query to_query() const { return query(); }
 
  protected:
   virtual pcq_query query() const = 0;
-  Context& ctx_;
+  Context* ctx_ = nullptr;
 };
 
 class BoundsSearcher : public Searcher {
  public:
   BoundsSearcher(Context& ctx, const AABB& bounds) : Searcher(ctx), bounds_(bounds) {}
+  explicit BoundsSearcher(const AABB& bounds) : bounds_(bounds) {}
 
  protected:
   pcq_query query() const override;
@@ -133,11 +137,46 @@ class BoundsSearcher : public Searcher {
 class ClassSearcher : public Searcher {
  public:
   ClassSearcher(Context& ctx, uint8_t cls) : Searcher(ctx), class_(cls) {}
+  explicit ClassSearcher(uint8_t cls) : class_(cls) {}
 
  protected:
   pcq_query query() const override;
   uint8_t class_;
 };
+
+// A group of GPUs of one box (pcq_group): files and point ranges of files shard across them, the results are those of
+// run_search_sequential / run_search_parallel over the whole file list (main.rs:122-183).
+class Group {
+ public:
+  explicit Group(uint32_t n_gpus);
+  ~Group();
+  Group(const Group&) = delete;
+  Group& operator=(const Group&) = delete;
+  pcq_group* get() const { return g_; }
+
+ private:
+  pcq_group* g_ = nullptr;
+};
+
+// what the collectors of one group search hold: one lane (sequential) or one per file (parallel)
+class GroupResult {
+ public:
+  explicit GroupResult(pcq_result* r) : r_(r) {}
+  ~GroupResult();
+  GroupResult(GroupResult&& o) noexcept : r_(o.r_) { o.r_ = nullptr; }
+  GroupResult(const GroupResult&) = delete;
+  GroupResult& operator=(const GroupResult&) = delete;
+  std::vector<uint64_t> counts() const;
+  // false for a CountCollector (`points()` == None)
+  bool points(uint32_t lane, const pcq_point** out, uint64_t* n) const;
+
+ private:
+  pcq_result* r_;
+};
+
+// kind: pcq_collector_kind; grid_bounds / cell_size as GridSampledCollector::new; per_file = one collector per file
+GroupResult search_files_on_group(Group& group, const std::vector<std::string>& paths, SearchImplementation impl,
+                                  const Searcher& searcher, int kind, const AABB* grid_bounds, double cell_size, bool per_file);
 
 // dump_points.rs
 class PointDumper {

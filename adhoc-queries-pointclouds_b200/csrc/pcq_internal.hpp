@@ -153,7 +153,7 @@ struct pcq_collector {
   uint64_t scan_hi = 0;       // end of the highest point range fed so far: the replay needs launches in scan order
   uint64_t prune_epoch = 0;   // bumped whenever candidates are dropped (prune / rehash)
   // group-wide replay of affected keys (group.cu): log-only passes append their launch logs here
-  bool log_only_mode = false;
+  int pass_mode = 0;  // 0 normal, 1 log-only (points of affected keys -> d_rawlog, nothing inserted), 2 sit this pass out
   Candidate* d_rawlog = nullptr;
   uint64_t rawlog_len = 0, rawlog_cap = 0;
   // finalisation keeps only the cells this collector owns: mix64(key) % own_parts == own_me (own_parts <= 1: all)

@@ -3,7 +3,8 @@
 // --optimized), same stdout lines, same collector / dumper choice and ordering rules.
 //
 // Differences, all deliberate: only the `--optimized` implementation exists here (the Regular path and
-// LAZ / LAZER inputs stay on the reference); `--gpu N` picks the device.
+// LAZ / LAZER inputs stay on the reference); `--gpu N` picks the device, `--gpus N` shards the files and point
+// ranges of the input over N GPUs of the box (pcq_group: same results, main.rs:122-183 semantics over the whole list).
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -55,7 +56,8 @@ void usage() {
       "        --parallel     Run search in parallel: one collector per file\n\nOPTIONS:\n"
       "        --bounds <BOUNDS>      \"minX;minY;minZ;maxX;maxY;maxZ\"\n        --class <CLASS>        8-bit unsigned class\n"
       "        --density <DENSITY>    Maximum density (minimum spacing) of the result\n    -i, --input <FILE>         file or directory\n"
-      "    -o, --output <OUTPUT>      output directory for matching_points_{k}.las\n        --gpu <N>              CUDA device (default 0)\n",
+      "    -o, --output <OUTPUT>      output directory for matching_points_{k}.las\n        --gpu <N>              CUDA device (default 0)\n"
+      "        --gpus <N>             shard files and point ranges over N GPUs of this box (default 1)\n",
       stderr);
 }
 
@@ -104,7 +106,7 @@ int main(int argc, char** argv) {
   std::string input, bounds_s, class_s, output, density_s;
   bool have_input = false, have_bounds = false, have_class = false, have_output = false, have_density = false;
   bool parallel = false, optimized = false;
-  int gpu = 0;
+  int gpu = 0, gpus = 1;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto value = [&](const char* name) -> std::string {
@@ -122,6 +124,7 @@ int main(int argc, char** argv) {
     else if (a == "--parallel") parallel = true;
     else if (a == "--optimized") optimized = true;
     else if (a == "--gpu") gpu = std::atoi(value("--gpu <N>").c_str());
+    else if (a == "--gpus") gpus = std::atoi(value("--gpus <N>").c_str());
     else if (a == "-h" || a == "--help") { usage(); return 0; }
     else {
       std::fprintf(stderr, "error: Found argument '%s' which wasn't expected, or isn't valid in this context\n", a.c_str());
@@ -183,6 +186,44 @@ int main(int argc, char** argv) {
     const bool timing = std::getenv("PCQ_CLI_TIMING") != nullptr;  // phase times on stderr (not part of the reference's output)
     auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     const double t_args = since_start();
+    const SearchImplementation impl = optimized ? SearchImplementation::Optimized : SearchImplementation::Regular;
+    double t_ctx = 0.0;
+    if (gpus > 1) {
+      // ---- a group of GPUs: every file is cut into point ranges, one per GPU; each GPU streams its ranges over its
+      // own PCIe link; counts are summed on the host, selected records concatenated in scan order, density cells
+      // exchanged by owner (group.cu).  Same collectors, same output rules.
+      Group group((uint32_t)gpus);
+      t_ctx = since_start();
+      std::unique_ptr<AABB> grid_bounds;
+      if (have_density) grid_bounds.reset(new AABB(bounds ? *bounds : get_total_bounds(input_files)));
+      std::unique_ptr<Searcher> searcher;  // (carries the predicate only: the group owns the device contexts)
+      if (bounds) searcher.reset(new BoundsSearcher(*bounds));
+      else searcher.reset(new ClassSearcher((uint8_t)klass));
+      std::unique_ptr<PointDumper> dumper;
+      if (have_output) dumper.reset(new FileDumper(output));
+      else dumper.reset(new IgnoreDumper());
+      const int kind = have_density ? PCQ_COLLECT_GRID : (have_output ? PCQ_COLLECT_BUFFER : PCQ_COLLECT_COUNT);
+      std::printf("Searching %zu files...\n", input_files.size());
+      std::fflush(stdout);
+      if (!input_files.empty()) {
+        GroupResult res = search_files_on_group(group, input_files, impl, *searcher, kind, grid_bounds.get(), density, parallel);
+        const std::vector<uint64_t> counts = res.counts();
+        if (kind == PCQ_COLLECT_COUNT) {
+          uint64_t total = 0;
+          for (uint64_t c : counts) total += c;
+          std::printf("Found %zu matching points\n", (size_t)total);
+        } else {
+          for (uint32_t lane = 0; lane < counts.size(); ++lane) {
+            const pcq_point* pts = nullptr;
+            uint64_t n = 0;
+            res.points(lane, &pts, &n);
+            dumper->dump_points(pts, n);
+          }
+        }
+      } else if (kind == PCQ_COLLECT_COUNT) {
+        std::printf("Found 0 matching points\n");
+      }
+    } else {
     // The process uses ONE GPU: hiding the others before the first CUDA call keeps the driver from initialising every
     // device of the box (seconds on an 8-GPU node; the reference's throughput line includes start-up, main.rs:192, 309-316)
     if (std::getenv("CUDA_VISIBLE_DEVICES") == nullptr) {
@@ -190,7 +231,7 @@ int main(int argc, char** argv) {
       gpu = 0;
     }
     Context ctx(gpu);
-    const double t_ctx = since_start();
+    t_ctx = since_start();
     std::unique_ptr<Searcher> searcher;
     if (bounds) searcher.reset(new BoundsSearcher(ctx, *bounds));
     else searcher.reset(new ClassSearcher(ctx, (uint8_t)klass));
@@ -208,8 +249,6 @@ int main(int argc, char** argv) {
     if (have_output) dumper.reset(new FileDumper(output));
     else dumper.reset(new IgnoreDumper());
 
-    const SearchImplementation impl = optimized ? SearchImplementation::Optimized : SearchImplementation::Regular;
-
     std::printf("Searching %zu files...\n", input_files.size());
     std::fflush(stdout);
 
@@ -220,6 +259,7 @@ int main(int argc, char** argv) {
     } else {
       std::unique_ptr<ResultCollector> collector = make_collector();
       run_search_sequential(input_files, *searcher, impl, *collector, *dumper);
+    }
     }
 
     if (timing)

@@ -148,7 +148,8 @@ int pcq_file_stage_host(pcq_ctx* ctx, const void* file_bytes, size_t n_bytes, co
 /* Wraps point data that is already resident in HBM.  For LAS `dev_point_data` points at record 0;
  * for LAST it points at the start of the transposed record block (column of the field at record
  * offset k starts at dev_point_data + k * desc->n_points, last_reader.rs:88-144).  The memory stays
- * owned by the caller and must come from an allocator with at least 16-byte granularity (cudaMalloc, a framework's
+ * owned by the caller, must not be rewritten while the file object (and its chunk index) is in use, and must come
+ * from an allocator with at least 16-byte granularity (cudaMalloc, a framework's
  * caching allocator, ...): record tiles move with 16-byte bulk copies, so up to 15 bytes past the last record may be
  * read.  `first_point_index` is the scan index of record 0 inside its file. */
 int pcq_file_wrap_device(pcq_ctx* ctx, const pcq_file_desc* desc, const void* dev_point_data,
@@ -192,7 +193,9 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
                      pcq_collector* const* collectors, uint32_t n_collectors);
 
 /* Host-staged variant: whole file images in (ideally pinned) host memory are streamed through a ring
- * of HBM chunk buffers, copies overlapped with the scan; nothing stays resident. */
+ * of HBM chunk buffers, copies overlapped with the scan; nothing stays resident.  A count search returns
+ * while its last copies and scans are still in flight: `file_bytes` must stay valid (and unchanged) until a
+ * collector of the call has been read or pcq_ctx_synchronize has returned. */
 int pcq_search_host_files(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes,
                           const char* const* exts, uint32_t n_files, const pcq_query* query,
                           pcq_collector* const* collectors, uint32_t n_collectors);
@@ -288,6 +291,96 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
                                uint64_t* counts /* n_parts */);
 /* Folds candidates received from peers (device pointer) into this collector's grid. */
 int pcq_grid_import_candidates(pcq_collector* c, const void* dev_candidates, uint64_t n);
+
+/* ---- multi-GPU: a group of GPUs of one box -----------------------------------------------------------------------
+ * The reference's only parallelism is one rayon task per file (run_search_parallel, main.rs:146-183).  Here files AND
+ * point ranges of files shard across the GPUs of one box.  Count queries need no exchange (the per-file counts are
+ * summed on the host, or with one ncclAllReduce of n_files integers when every GPU has its own process); select
+ * queries concatenate the per-(file, GPU) record streams in GPU order, which is the order one BufferCollector would
+ * have seen; a max-density query has one exchange step: one candidate per locally occupied cell travels to the cell's
+ * owner (mix64(key) % holders) with a grouped ncclSend / ncclRecv all-to-all over NVLink, ties break on the global
+ * scan index, and the points of SparseGrid keys that suffer key aliasing (whose result is a sequential fold in scan
+ * order, grid_sampling.rs:62-102) are routed to the key's owner and folded there in global scan order — so every
+ * result equals what the reference computes over the whole dataset.
+ *
+ * A group is ONE process driving n GPUs (pcq_group_create; ncclCommInitAll) or one process per GPU
+ * (pcq_group_create_rank; the launcher hands the id of pcq_group_unique_id to every rank).  In the second form every
+ * entry point below is collective: all ranks call it with the same arguments.  NCCL is resolved at run time
+ * (dlopen of libnccl.so.2, or the path in PCQ_NCCL_LIB); a group of one GPU does not need it.                   */
+typedef struct pcq_group pcq_group;
+typedef struct pcq_dataset pcq_dataset; /* files sharded over the members of a group, resident in HBM          */
+typedef struct pcq_result pcq_result;   /* what the collectors of one group search hold, per lane               */
+
+#define PCQ_GROUP_ID_BYTES 128
+
+int pcq_group_create(const int* devices /* NULL: 0 .. n-1 */, uint32_t n_devices, pcq_group** out);
+int pcq_group_unique_id(void* id_out /* PCQ_GROUP_ID_BYTES */);
+int pcq_group_create_rank(int device, uint32_t rank, uint32_t world, const void* id, pcq_group** out);
+void pcq_group_destroy(pcq_group* g);
+uint32_t pcq_group_world(const pcq_group* g);
+uint32_t pcq_group_local_count(const pcq_group* g);                      /* members driven by this process      */
+uint32_t pcq_group_local_rank(const pcq_group* g, uint32_t local_index); /* their ranks in the group            */
+pcq_ctx* pcq_group_ctx(pcq_group* g, uint32_t local_index);              /* their contexts (owned by the group) */
+uint64_t pcq_group_launch_count(const pcq_group* g);
+int pcq_group_synchronize(pcq_group* g);
+
+/* How a dataset is cut (host only, no GPU).  PCQ_SHARD_RANGES: every file is cut into `world` contiguous ranges of
+ * whole index chunks and rank r takes the r-th range of every file, so that a query which touches few files (doc-S:
+ * 5 of 64 tiles) still spreads over all GPUs.  PCQ_SHARD_FILES: whole files, largest first onto the least loaded
+ * rank (the reference's unit of parallelism).  Writes the first `cap` shards, ordered by (file, rank).          */
+enum pcq_shard_mode { PCQ_SHARD_RANGES = 0, PCQ_SHARD_FILES = 1 };
+typedef struct pcq_shard {
+  uint32_t file;
+  uint32_t rank;
+  uint64_t first_point;
+  uint64_t n_points;
+} pcq_shard;
+int pcq_shard_plan(const uint64_t* points_per_file, uint32_t n_files, uint32_t world, int mode, pcq_shard* out,
+                   uint64_t cap, uint64_t* n_out);
+
+/* Stages every member's shards of whole file images (host memory) into its HBM. */
+int pcq_group_stage_host_files(pcq_group* g, const void* const* file_bytes, const size_t* n_bytes,
+                               const char* const* exts, uint32_t n_files, int shard_mode, pcq_dataset** out);
+/* A dataset of point ranges that are already resident (pcq_file_wrap_device / pcq_file_stage_host on the contexts of
+ * pcq_group_ctx): piece i is files[i], a range of file file_index[i], held by local member local_member[i].  A
+ * member holds at most one range of a file, pieces of a member in ascending file order, ranges of a file ascending
+ * with the rank.  points_per_file describes the WHOLE dataset (all n_files files).  The files stay the caller's. */
+int pcq_group_wrap_files(pcq_group* g, const uint64_t* points_per_file, uint32_t n_files, pcq_file* const* files,
+                         const uint32_t* local_member, const uint32_t* file_index, uint32_t n_local,
+                         pcq_dataset** out);
+void pcq_dataset_release(pcq_dataset* ds);
+
+/* run_search_sequential (per_file == 0: ONE collector over all files in dataset order, main.rs:122-144) or
+ * run_search_parallel (per_file != 0: one collector per file, main.rs:146-183) of a batch of queries over a resident
+ * dataset, with collectors of `collector_kind` (gmin / gmax / cell_size as in pcq_collector_create).  out[q] receives
+ * the result of query q.  Count searches return before their kernels finish; pcq_result_counts waits.            */
+int pcq_group_search(pcq_group* g, pcq_dataset* ds, const pcq_query* queries, uint32_t n_queries, int collector_kind,
+                     const double gmin[3], const double gmax[3], double cell_size, int per_file, pcq_result** out);
+/* The same over file images in host memory (pcq_search_host_files_multi per member, restricted to its shards): every
+ * member streams its point ranges over its own PCIe link.  A process only reads the headers and the ranges of its own
+ * members, so with one process per GPU an image needs to be populated (and pinned, pcq_host_register) only there.
+ * Synchronous: the images may be released when the call returns.                                                  */
+int pcq_group_search_host_files(pcq_group* g, const void* const* file_bytes, const size_t* n_bytes,
+                                const char* const* exts, uint32_t n_files, const pcq_query* queries, uint32_t n_queries,
+                                int collector_kind, const double gmin[3], const double gmax[3], double cell_size,
+                                int per_file, int shard_mode, pcq_result** out);
+
+/* ResultCollector::point_count per lane (1 lane, or one per file), group-wide. */
+int pcq_result_counts(pcq_result* r, const uint64_t** counts, uint32_t* n_lanes);
+/* ResultCollector::points of a lane: BUFFER in scan order, GRID in arbitrary order; COUNT: NULL / 0.  With one
+ * process per GPU the records are gathered on rank 0 (other ranks get NULL / 0; the counts are known everywhere).
+ * Pinned host memory owned by the result.                                                                        */
+int pcq_result_points(pcq_result* r, uint32_t lane, const pcq_point** out_points, uint64_t* out_n);
+void pcq_result_release(pcq_result* r);
+
+/* Pins (page-locks) a range of host memory the caller owns — e.g. the mapping of a file — so that the host-staged
+ * searches copy from it at link speed instead of through the bounce ring. */
+int pcq_host_register(void* p, size_t n_bytes);
+int pcq_host_unregister(void* p);
+/* Binds the calling thread (and the memory it touches first from now on) to the NUMA node the context's GPU hangs
+ * off, so that pinned staging buffers are local to the GPU's PCIe root.  *out_node: the node, or -1 when the platform
+ * does not say.  Linux only; a no-op elsewhere. */
+int pcq_ctx_bind_host_thread(pcq_ctx* ctx, int* out_node);
 
 #ifdef __cplusplus
 }
