@@ -110,6 +110,11 @@ class ScanStats(C.Structure):
     ]
 
 
+class GroupStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("scan_ms", "rescan_ms", "export_ms", "exchange_ms", "import_ms", "finalize_ms")] + \
+               [(n, C.c_uint64) for n in ("cells_sent", "log_entries_sent", "bytes_sent", "affected_keys")]
+
+
 class PcqError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"pcq error {code}: {message}")
@@ -180,6 +185,7 @@ def _load() -> C.CDLL:
         "pcq_group_ctx": (vp, [vp, u32]),
         "pcq_group_launch_count": (u64, [vp]),
         "pcq_group_synchronize": (C.c_int, [vp]),
+        "pcq_group_last_stats": (C.c_int, [vp, P(GroupStats)]),
         "pcq_shard_plan": (C.c_int, [P(u64), u32, u32, C.c_int, vp, u64, P(u64)]),
         "pcq_group_stage_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, C.c_int, P(vp)]),
         "pcq_group_wrap_files": (C.c_int, [vp, P(u64), u32, P(vp), P(u32), P(u32), u32, P(vp)]),

@@ -24,6 +24,7 @@
 #include <nccl.h>  // types and enums only: every function is resolved with dlsym
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -182,6 +183,7 @@ struct pcq_group {
   // COUNT searches return before their kernels finish; their counts land in the members' pinned h_counts, which the
   // next search reuses: results still pending when another search starts are completed first
   std::vector<pcq_result*> pending;
+  pcq_group_stats stats{};  // phases of the last select / density search
 };
 
 struct pcq_dataset {
@@ -213,6 +215,16 @@ struct pcq_result {
 };
 
 namespace {
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int sync_members(pcq_group* g) {
+  for (Member& M : g->local) {
+    RC(use_device(M.ctx));
+    CU(cudaStreamSynchronize(M.ctx->stream));
+  }
+  return PCQ_OK;
+}
 
 int member_index_of_rank(const pcq_group* g, uint32_t rank) {
   for (size_t m = 0; m < g->local.size(); ++m)
@@ -601,6 +613,8 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
   const uint32_t W = g->world;
   const size_t nl = g->local.size();
   std::vector<std::vector<Stream>> streams(nl);
+  pcq_group_stats& st = g->stats;
+  double t0 = now_ms();
   if (W > 1) {
     if (g->use_nccl) RC(load_nccl());
     // 1. affected keys (key aliasing, alias.cu) of every lane, group-wide
@@ -653,7 +667,10 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
       for (size_t m = 0; m < nl; ++m)
         for (pcq_collector* c : runs[m].cols) c->pass_mode = 0;
       RC(rc);
+      for (const std::vector<uint64_t>& v : lane_keys) st.affected_keys += v.size();
     }
+    st.rescan_ms += now_ms() - t0;
+    t0 = now_ms();
 
     // 3. export: one candidate per locally occupied cell, partitioned by owner among the holders of the lane
     struct Exp {
@@ -691,6 +708,8 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
         }
       }
     }
+    st.export_ms += now_ms() - t0;
+    t0 = now_ms();
     // 4. everybody learns every part size: sizes[(rank * n_int + lane) * 2W + 2 * owner rank + {0: cells, 1: log}]
     const size_t L = (size_t)n_int * 2 * W;
     std::vector<std::vector<uint64_t>> mine(nl, std::vector<uint64_t>(L, 0));
@@ -770,6 +789,22 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
         }
       }
     RC(all_to_all(g, sends, recvs));
+    RC(sync_members(g));
+    for (size_t m = 0; m < nl; ++m)
+      for (const Part& p : sends[m]) {
+        st.bytes_sent += p.bytes;
+      }
+    for (size_t m = 0; m < nl; ++m)
+      for (size_t i = 0; i < runs[m].cols.size(); ++i) {
+        const std::vector<uint32_t>& H = holders[runs[m].lane_of[i]];
+        for (size_t h = 0; h < H.size(); ++h)
+          if (H[h] != g->local[m].rank) {
+            st.cells_sent += exps[m][i].counts[h];
+            st.log_entries_sent += exps[m][i].log_counts[h];
+          }
+      }
+    st.exchange_ms += now_ms() - t0;
+    t0 = now_ms();
     // 6. owners fold what they received: cells into their own table (their own part is already there), raw log
     //    entries — together with their own — through the ordered replay
     RC(for_each_member(g, [&](uint32_t m) -> int {
@@ -809,6 +844,8 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
       return PCQ_OK;
     }));
   }
+  if (W > 1) st.import_ms += now_ms() - t0;
+  t0 = now_ms();
   // 7. every owner's winners -> the result
   RC(for_each_member(g, [&](uint32_t m) -> int {
     for (size_t i = 0; i < runs[m].cols.size(); ++i) {
@@ -819,7 +856,9 @@ int combine_grid(pcq_group* g, uint32_t n_int, bool per_file, const std::vector<
     }
     return PCQ_OK;
   }));
-  return gather_records(g, n_int, per_file, streams, res);
+  const int grc = gather_records(g, n_int, per_file, streams, res);
+  st.finalize_ms += now_ms() - t0;
+  return grc;
 }
 
 int check_query_args(pcq_group* g, const pcq_query* q, uint32_t n_queries, int kind, const double* gmin, const double* gmax) {
@@ -1025,6 +1064,12 @@ uint64_t pcq_group_launch_count(const pcq_group* g) {
   if (g)
     for (const Member& M : g->local) n += M.ctx ? M.ctx->launches : 0;
   return n;
+}
+
+int pcq_group_last_stats(const pcq_group* g, pcq_group_stats* out) {
+  if (!g || !out) return fail(PCQ_ERR_ARG, "null argument");
+  *out = g->stats;
+  return PCQ_OK;
 }
 
 int pcq_group_synchronize(pcq_group* g) {
@@ -1239,11 +1284,14 @@ int pcq_group_search(pcq_group* g, pcq_dataset* ds, const pcq_query* queries, ui
     }
     if (rc == PCQ_OK) rc = combine_counts(g, F, runs, res.data());
   } else if (rc == PCQ_OK) {
+    g->stats = pcq_group_stats{};
+    const double t_scan = now_ms();
     rc = for_each_member(g, [&](uint32_t m) -> int {
       RC(prepare_member(m));
       for (uint32_t q = 0; q < n_queries; ++q) RC(search_member(m, q));
-      return PCQ_OK;
+      return pcq_ctx_synchronize(g->local[m].ctx);
     });
+    g->stats.scan_ms = now_ms() - t_scan;
     for (uint32_t q = 0; q < n_queries && rc == PCQ_OK; ++q) {
       if (collector_kind == PCQ_COLLECT_BUFFER) {
         std::vector<std::vector<Stream>> streams(nl);
@@ -1320,6 +1368,8 @@ int pcq_group_search_host_files(pcq_group* g, const void* const* file_bytes, con
     return search_host_multi(M.ctx, file_bytes, n_bytes, exts, F, queries + q0, nq, cols[m].data() + (size_t)q0 * cols_per_query,
                              cols_per_query, nullptr, ranges[m].data());
   };
+  g->stats = pcq_group_stats{};
+  const double t_scan = now_ms();
   int rc = for_each_member(g, [&](uint32_t m) -> int {
     Member& M = g->local[m];
     RC(use_device(M.ctx));
@@ -1340,8 +1390,10 @@ int pcq_group_search_host_files(pcq_group* g, const void* const* file_bytes, con
           }
       }
     }
-    return search_member(m, 0, n_queries);
+    RC(search_member(m, 0, n_queries));
+    return collector_kind == PCQ_COLLECT_COUNT ? PCQ_OK : pcq_ctx_synchronize(M.ctx);
   });
+  g->stats.scan_ms = now_ms() - t_scan;
   if (rc == PCQ_OK && W > 1 && !g->one_process) rc = load_nccl();
   for (uint32_t q = 0; q < n_queries; ++q) out[q] = nullptr;
   for (uint32_t q = 0; q < n_queries && rc == PCQ_OK; ++q) rc = new_result(collector_kind, per_file != 0, F, &out[q]);

@@ -145,6 +145,12 @@ class Group:
     def synchronize(self):
         check(lib.pcq_group_synchronize(self.handle))
 
+    @property
+    def last_stats(self) -> dict:
+        st = B.GroupStats()
+        check(lib.pcq_group_last_stats(self.handle, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in B.GroupStats._fields_}
+
     # ---- datasets ------------------------------------------------------------------------------------------------
     def stage_host_files(self, images: Sequence[tuple], shard_mode: int = B.SHARD_RANGES) -> Dataset:
         n = len(images)

@@ -373,6 +373,22 @@ int pcq_result_counts(pcq_result* r, const uint64_t** counts, uint32_t* n_lanes)
 int pcq_result_points(pcq_result* r, uint32_t lane, const pcq_point** out_points, uint64_t* out_n);
 void pcq_result_release(pcq_result* r);
 
+/* Where the time of the last select / density search of the group went (host clock around synchronised phases, this
+ * process's members; a count search does not synchronise and leaves them untouched). */
+typedef struct pcq_group_stats {
+  double scan_ms;            /* the members' scans of their ranges (first pass)                                   */
+  double rescan_ms;          /* density: gathering the affected keys + the log-only second pass (0 when none)     */
+  double export_ms;          /* density: one candidate per locally occupied cell, partitioned by owner            */
+  double exchange_ms;        /* density: part sizes + the all-to-all over NVLink                                  */
+  double import_ms;          /* density: owners fold what they received (+ the ordered replay of affected keys)   */
+  double finalize_ms;        /* winners -> 31-byte records -> host lanes                                          */
+  uint64_t cells_sent;       /* candidates that left their GPU                                                    */
+  uint64_t log_entries_sent; /* points of affected keys that left their GPU                                       */
+  uint64_t bytes_sent;       /* 64 bytes each                                                                     */
+  uint64_t affected_keys;    /* SparseGrid keys with an order-dependent result, group-wide                        */
+} pcq_group_stats;
+int pcq_group_last_stats(const pcq_group* g, pcq_group_stats* out);
+
 /* Pins (page-locks) a range of host memory the caller owns — e.g. the mapping of a file — so that the host-staged
  * searches copy from it at link speed instead of through the bounce ring. */
 int pcq_host_register(void* p, size_t n_bytes);
