@@ -184,6 +184,15 @@ struct pcq_group {
   // next search reuses: results still pending when another search starts are completed first
   std::vector<pcq_result*> pending;
   pcq_group_stats stats{};  // phases of the last select / density search
+  // Pinned host buffers of the results are recycled: page-locking tens of megabytes costs more than the search that
+  // fills them (~1 ms per MB on a virtualised host), so a released result hands its buffer back to the group.
+  struct HostBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool in_use = false;
+  };
+  std::vector<HostBuf> host_pool;
+  std::vector<pcq_result*> live;  // results that hold a pool buffer (orphaned if the group goes first)
 };
 
 struct pcq_dataset {
@@ -204,7 +213,8 @@ struct pcq_result {
   uint32_t n_lanes = 0;
   std::vector<uint64_t> counts;       // per lane, group-wide
   std::vector<uint64_t> lane_off;     // records: first record of the lane within `points` (n_lanes + 1 entries)
-  uint8_t* points = nullptr;          // pinned host memory, 31-byte records
+  uint8_t* points = nullptr;          // pinned host memory (a buffer of the group's pool), 31-byte records
+  pcq_group* owner = nullptr;         // whose pool `points` came from
   uint64_t n_points_held = 0;         // records this process holds (rank 0's process: all of them)
   bool has_points = false;
   // a COUNT search returns before its kernels finish: the counts land in h_counts[count_slot ...] of the members
@@ -492,6 +502,51 @@ int finish_pending(pcq_group* g) {
   return PCQ_OK;
 }
 
+// pinned host buffer for a result: the smallest free pool buffer that fits, else a new one (a few spares are kept)
+int pool_acquire(pcq_group* g, size_t bytes, pcq_result* res) {
+  int best = -1;
+  for (size_t i = 0; i < g->host_pool.size(); ++i) {
+    const pcq_group::HostBuf& b = g->host_pool[i];
+    if (!b.in_use && b.cap >= bytes && (best < 0 || b.cap < g->host_pool[best].cap)) best = (int)i;
+  }
+  if (best < 0) {
+    // drop free buffers that are too small before pinning more
+    for (pcq_group::HostBuf& b : g->host_pool)
+      if (!b.in_use && b.p) {
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+      }
+    pcq_group::HostBuf nb;
+    nb.cap = round_up(bytes + bytes / 8, 1u << 20);
+    if (cudaMallocHost(reinterpret_cast<void**>(&nb.p), nb.cap) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PCQ_ERR_NOMEM, "cannot pin %zu bytes of host memory for the result", nb.cap);
+    }
+    size_t slot = g->host_pool.size();
+    for (size_t i = 0; i < g->host_pool.size(); ++i)
+      if (!g->host_pool[i].p) slot = i;
+    if (slot == g->host_pool.size()) g->host_pool.push_back(nb);
+    else g->host_pool[slot] = nb;
+    best = (int)slot;
+  }
+  g->host_pool[best].in_use = true;
+  res->points = g->host_pool[best].p;
+  res->owner = g;
+  g->live.push_back(res);
+  return PCQ_OK;
+}
+
+void pool_release(pcq_result* res) {
+  pcq_group* g = res->owner;
+  if (!g || !res->points) return;
+  for (pcq_group::HostBuf& b : g->host_pool)
+    if (b.p == res->points) b.in_use = false;
+  g->live.erase(std::remove(g->live.begin(), g->live.end(), res), g->live.end());
+  res->points = nullptr;
+  res->owner = nullptr;
+}
+
 // ---- records of every (member, lane) -> host lanes in member order ---------------------------------------------------
 struct Stream {  // records one local member holds for one lane, in HBM
   uint32_t lane;
@@ -532,10 +587,7 @@ int gather_records(pcq_group* g, uint32_t n_int, bool per_file, const std::vecto
     res->n_points_held = 0;
   } else {
     res->n_points_held = total;
-    if (total && cudaMallocHost(reinterpret_cast<void**>(&res->points), total * 31ull) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(PCQ_ERR_NOMEM, "cannot pin %llu bytes of host memory for the result", (unsigned long long)(total * 31ull));
-    }
+    if (total) RC(pool_acquire(g, total * 31ull, res));
   }
   auto place = [&](uint32_t lane, uint32_t rank) -> uint64_t {  // first record of (lane, rank) in the host buffer
     uint64_t o = lane_off[lane];
@@ -937,6 +989,16 @@ static int group_finish_create(pcq_group* g) {
 void pcq_group_destroy(pcq_group* g) {
   if (!g) return;
   finish_pending(g);
+  // results that outlive their group keep their counts and lose their records
+  for (pcq_result* r : g->live) {
+    r->points = nullptr;
+    r->owner = nullptr;
+    r->has_points = false;
+    r->lane_off.assign(r->n_lanes + 1, 0);
+  }
+  g->live.clear();
+  for (pcq_group::HostBuf& b : g->host_pool)
+    if (b.p) cudaFreeHost(b.p);
   for (Member& M : g->local) {
     if (M.ctx) {
       cudaSetDevice(M.device);
@@ -1188,7 +1250,7 @@ int pcq_group_wrap_files(pcq_group* g, const uint64_t* points_per_file, uint32_t
 void pcq_result_release(pcq_result* r) {
   if (!r) return;
   if (r->pending_group) finish_counts(r);
-  if (r->points) cudaFreeHost(r->points);
+  pool_release(r);
   delete r;
 }
 

@@ -26,6 +26,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include <cstdint>
 
@@ -313,8 +314,9 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 // warp covers 32 consecutive descriptors (256 bytes).
 constexpr int kLookback = 8;
 
-__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* state, uint64_t tile,
-                                                                 uint64_t lane_first_tile) {
+template <bool WAIT = true>
+__device__ __forceinline__ bool lookback_window(const unsigned long long* state, uint64_t tile, uint64_t lane_first_tile,
+                                                unsigned long long& excl_out) {
   unsigned long long excl = 0;
   long long hi = (long long)tile - 1;
   const long long lo = (long long)lane_first_tile;
@@ -330,7 +332,11 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
         sv[k] = t >= lo ? ld_state(state + t * (long long)kDescStride) : (kStPrefix << kStatusShift);  // below the lane start: prefix 0
         pending |= (sv[k] >> kStatusShift) == 0ull;
       }
-    } while (__any_sync(0xffffffffu, pending));
+      pending = __any_sync(0xffffffffu, pending);
+      // (a descriptor that is not ready only matters when it lies above the closest prefix; waiting for all of the
+      // window is simpler and the window is published within the same microsecond)
+      if (!WAIT && pending) return false;
+    } while (pending);
     // closest descriptor that already carries an inclusive prefix: row kf, lane lf
     int kf = kLookback;
     uint32_t lf = 32u;
@@ -353,8 +359,17 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     excl += v;
     if (pm != 0u) break;
+    if (!WAIT) return false;  // one window, one round trip: no prefix in reach
     hi -= 32 * kLookback;
   }
+  excl_out = excl;
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* state, uint64_t tile,
+                                                                 uint64_t lane_first_tile) {
+  unsigned long long excl = 0;
+  lookback_window<true>(state, tile, lane_first_tile, excl);
   return excl;
 }
 
@@ -468,29 +483,65 @@ struct QueueFetch {
   __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return qe[j]->gidx; }
 };
 
-// rare path, kept out of line so that it costs the insert kernel neither registers nor instruction-cache space
-template <class Fetch>
-__device__ __noinline__ void grid_log_point(const GridDev& g, const Segment& S, const Fetch& f, int j, uint64_t key) {
-  const unsigned long long li = atomicAdd(g.log_count, 1ull);
-  if (li < g.log_cap) {
-    uint32_t w[8];
-    f.words(S, j, w);
-    uint4* c4 = reinterpret_cast<uint4*>(g.log + li);
-    const unsigned long long gidx = f.gidx(S, j);
+// rare path, kept out of line so that it costs the insert kernel neither registers nor instruction-cache space.
+// Everything travels BY VALUE: a reference to the caller's point registers would force them into local memory, for
+// every point of every tile (that was 1.8 GB of local stores per navvis-XL launch).
+__device__ __noinline__ void grid_log_entry(Candidate* log, unsigned long long* log_count, uint64_t log_cap, uint32_t* flags,
+                                            uint64_t key, unsigned long long gidx, uint4 wa, uint4 wb) {
+  const unsigned long long li = atomicAdd(log_count, 1ull);
+  if (li < log_cap) {
+    uint4* c4 = reinterpret_cast<uint4*>(log + li);
     c4[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), 0u, 0u);
-    c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
-    c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
-    c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
+    c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), wa.x, wa.y);
+    c4[2] = make_uint4(wa.z, wa.w, wb.x, wb.y);
+    c4[3] = make_uint4(wb.z, wb.w & 0x00FFFFFFu, 0u, 0u);
   } else {
-    atomicOr(g.flags, kFlagLogOverflow);
+    atomicOr(flags, kFlagLogOverflow);
   }
 }
+template <class Fetch>
+__device__ __forceinline__ void grid_log_point(const GridDev& g, const Segment& S, const Fetch& f, int j, uint64_t key) {
+  uint32_t w[8];
+  f.words(S, j, w);
+  grid_log_entry(g.log, g.log_count, g.log_cap, g.flags, key, f.gidx(S, j), make_uint4(w[0], w[1], w[2], w[3]),
+                 make_uint4(w[4], w[5], w[6], w[7]));
+}
 
-// Warp-convergent: every lane calls it; m[j] says whether this lane's j-th point of the tile matches.
-// A point survives as a candidate iff its distance is <= the cell minimum seen so far; the true
-// winner (smallest distance, then smallest scan index == the strict `<` fold of :97-102) always is.
-// The kPPT points of a lane are taken through each step together so that their table reads (random
-// accesses into a table far larger than L2) are in flight at the same time.
+// L2 residency of the density insert: the cell table is the one structure that is re-read (every matching point reads
+// its cell), while records stream through once and candidates are written once — table accesses ask L2 to keep their
+// lines (evict_last), candidate stores not to (evict_first), so that a table whose touched sectors fit L2 stays there.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_stream_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long ld_table(const unsigned long long* p, uint64_t pol) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_min_table(unsigned long long* p, unsigned long long v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+// One whole 32-byte sector per store (sm_100: 256-bit st.global, SASS STG.256): half the store instructions of four
+// 16-byte stores per 64-byte candidate, and no half-written sectors in L2.
+__device__ __forceinline__ void stg_sector_stream(void* p, const uint4& a, const uint4& b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol)
+               : "memory");
+}
+
+// Warp-convergent: every lane calls it; m[j] says whether this lane's j-th point matches.
+// A point survives as a *candidate* iff its distance is <= the cell minimum it reads (a possibly stale value that is
+// never below the true minimum, so the true winner — smallest distance, then smallest scan index == the strict `<`
+// fold of :97-102 — always survives); the minimum itself is maintained with a fire-and-forget red.min, so nothing
+// waits for an atomic's round trip.  The kPPT points of a lane are taken through each step together so that their
+// table reads are in flight at the same time.
 template <class Fetch>
 __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment& S, const bool (&m)[kPPT], const Fetch& f,
                                                  CandChunk& ch) {
@@ -498,28 +549,30 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) any_m |= m[j];
   if (!__any_sync(0xffffffffu, any_m)) return;  // most tiles of a small query box hold no match at all
-  CellEval e[kPPT];
-  uint64_t slot[kPPT];
+  const uint64_t keep = l2_keep_policy(), stream = l2_stream_policy();
+  uint64_t key[kPPT], slot[kPPT];
+  unsigned long long dist[kPPT], seen[kPPT];
   bool live[kPPT];
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) {
     live[j] = false;
     slot[j] = 0;
-    e[j].key = 0;
-    e[j].dist_bits = 0;
-    e[j].aliased = false;
+    key[j] = 0;
+    dist[j] = 0ull;
     if (m[j]) {
       int32_t vx, vy, vz;
       f.xyz(j, vx, vy, vz);
       const double px = reconstruct(vx, S.scale[0], S.offset[0]);
       const double py = reconstruct(vy, S.scale[1], S.offset[1]);
       const double pz = reconstruct(vz, S.scale[2], S.offset[2]);
-      e[j] = grid_eval(g, px, py, pz);
-      if (e[j].aliased || alias_find(g, e[j].key) != ~0u) {
+      const CellEval e = grid_eval(g, px, py, pz);
+      key[j] = e.key;
+      dist[j] = e.dist_bits;
+      if (e.aliased || alias_find(g, e.key) != ~0u) {
         // a point of an affected key: logged for the ordered replay, never enters the table
-        grid_log_point(g, S, f, j, e[j].key);
+        grid_log_point(g, S, f, j, e.key);
       } else if (!g.log_only) {
-        slot[j] = grid_slot(g, e[j].key, true);
+        slot[j] = grid_slot(g, e.key, true);
         if (slot[j] == ~0ull)
           atomicOr(g.flags, kFlagHashFull);
         else
@@ -527,23 +580,19 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
       }
     }
   }
-  // The cell minimum only ever decreases, so a (possibly stale) plain read that is already smaller than this
-  // point's distance proves the point can never win: skip the atomic.  In dense data (many points per cell)
-  // that removes most of the read-modify-write traffic.
-  unsigned long long seen[kPPT];
+  // both table reads of a lane are in flight together (random accesses into a table far larger than L1)
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) {
     seen[j] = 0ull;
-    if (live[j]) seen[j] = __ldcg(g.table + slot[j]);
+    if (live[j]) seen[j] = ld_table(g.table + slot[j], keep);
   }
   bool want[kPPT];
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) {
-    want[j] = false;
-    if (live[j] && e[j].dist_bits <= seen[j]) {
-      const unsigned long long old = atomicMin(g.table + slot[j], e[j].dist_bits);
-      want[j] = e[j].dist_bits <= old;
-    }
+    // The cell minimum only ever decreases, so a (possibly stale) read that is already smaller than this point's
+    // distance proves the point can never win: no atomic, no candidate.  In dense data that is most points.
+    want[j] = live[j] && dist[j] <= seen[j];
+    if (want[j] && dist[j] < seen[j]) red_min_table(g.table + slot[j], dist[j], keep);
   }
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) {
@@ -557,10 +606,9 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
         f.words(S, j, w);
         uint4* c4 = reinterpret_cast<uint4*>(g.cands + ci);
         const unsigned long long gidx = f.gidx(S, j);
-        c4[0] = make_uint4((uint32_t)e[j].key, (uint32_t)(e[j].key >> 32), (uint32_t)e[j].dist_bits, (uint32_t)(e[j].dist_bits >> 32));
-        c4[1] = make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]);
-        c4[2] = make_uint4(w[2], w[3], w[4], w[5]);
-        c4[3] = make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u);
+        stg_sector_stream(c4, make_uint4((uint32_t)key[j], (uint32_t)(key[j] >> 32), (uint32_t)dist[j], (uint32_t)(dist[j] >> 32)),
+                          make_uint4((uint32_t)gidx, (uint32_t)(gidx >> 32), w[0], w[1]), stream);
+        stg_sector_stream(c4 + 2, make_uint4(w[2], w[3], w[4], w[5]), make_uint4(w[6], w[7] & 0x00FFFFFFu, 0u, 0u), stream);
       } else {
         atomicOr(g.flags, kFlagCandOverflow);
       }
@@ -805,6 +853,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// the same with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the time is up
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra SWAIT_DONE;\n"
+      "bra SWAIT_LOOP;\n"
+      "SWAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(2000u)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // LAST positions (12-byte records) in count mode: 1024-record tiles, each thread takes 4 consecutive records with
 // three conflict-free 16-byte shared loads — a quarter of the load instructions of the generic path, which is what
 // a 12-byte-per-point scan needs to stay memory- rather than issue-bound.
@@ -940,6 +1019,210 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_grid_scan — the density scan (MODE_GRID) as a warp-specialised kernel.
+//
+// k_scan_staged ends every tile with a CTA-wide barrier (its producer is also a consumer), which is free for a count
+// but not for the density insert: a tile's insert is a chain of long-latency operations (table read, atomic,
+// candidate stores), and the barrier made every warp of the CTA wait for the slowest one, tile after tile (10 % of
+// the samples on the barrier, 25 % on the scoreboards behind it).  Here a PRODUCER warp streams record tiles into a
+// ring with bulk async copies and eight CONSUMER warps meet it on mbarriers only: a consumer copies the fields of
+// its 64 records of a tile into registers, releases the stage at once and then runs its insert on its own, so the
+// warps of a CTA drift apart and one warp's table misses are covered by the others' arithmetic.
+// QUEUE = true (sparse matches, chosen by the host like MODE_GRIDQ): matching points are appended to a per-warp queue
+// in shared memory (no atomics: the warp is the only writer) and inserted 64 at a time with every lane busy.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGsWarps = kTilePts / 64;           // consumer warps: 64 records of a tile each
+constexpr int kGsThreads = (kGsWarps + 1) * 32;   // + the producer warp
+constexpr uint32_t kGsQFlush = 64;                // insert when a warp has queued this many matches
+constexpr uint32_t kGsQCap = kGsQFlush - 1u + 64u + 1u;  // one more tile always fits
+
+// the two points of a lane, held in registers (the stage they came from is long gone when they are inserted)
+struct RegFetch {
+  int32_t x[kPPT], y[kPPT], z[kPPT];
+  uint32_t rg[kPPT], bc[kPPT];  // r | g << 16,  b | cls << 16
+  unsigned long long gi[kPPT];
+  __device__ __forceinline__ void xyz(int j, int32_t& vx, int32_t& vy, int32_t& vz) const {
+    vx = x[j];
+    vy = y[j];
+    vz = z[j];
+  }
+  __device__ __forceinline__ void words(const Segment& S, int j, uint32_t w[8]) const {
+    Hit h;
+    h.x = x[j];
+    h.y = y[j];
+    h.z = z[j];
+    h.cls = bc[j] >> 16;
+    const uint32_t rgb[3] = {rg[j] & 0xFFFFu, rg[j] >> 16, bc[j] & 0xFFFFu};
+    point_words(S, h, rgb, w);
+  }
+  __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return gi[j]; }
+};
+
+template <int R, int STAGES, bool QUEUE>
+__global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanParams P) {
+  constexpr uint32_t kTileBytes = (uint32_t)kTilePts * (uint32_t)R;
+  extern __shared__ __align__(128) uint8_t dsm[];  // STAGES * kTileBytes [+ kGsWarps * kGsQCap queue entries]
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ unsigned long long st_tile[STAGES];
+  __shared__ uint32_t st_segi[STAGES];
+  __shared__ Segment st_seg[STAGES];
+  __shared__ Segment wseg[kGsWarps];
+
+  const uint32_t wid = warp_id(), ln = lane_id();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1u);
+      mbar_init(&empty_bar[s], (uint32_t)kGsWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (wid == (uint32_t)kGsWarps) {
+    // ---------------- producer warp ----------------
+    uint64_t stream_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
+    uint32_t seg = 0;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t s = it % STAGES;
+      // (every consumer has left the stage; the producer has nothing else to do, so it sleeps in the wait instead of
+      // spinning: its polling was 9 % of the kernel's issued instructions)
+      if (it >= (uint32_t)STAGES) mbar_wait_sleepy(&empty_bar[s], ((it / STAGES) - 1u) & 1u);
+      const uint64_t tile = (uint64_t)blockIdx.x + (uint64_t)it * (uint64_t)gridDim.x;
+      if (tile >= P.n_tiles) {
+        if (ln == 0) {
+          st_tile[s] = ~0ull;
+          mbar_arrive(&full_bar[s]);
+        }
+        break;
+      }
+      seg = seg_forward(P, seg, tile);
+      const Segment* sg = P.segs + seg;
+      {  // the tile's segment travels with it: consumers are not in step with each other
+        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
+        uint32_t* dstw = reinterpret_cast<uint32_t*>(&st_seg[s]);
+        for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+      }
+      __syncwarp();
+      if (ln == 0) {
+        const uint64_t p0 = (tile - sg->first_tile) * (uint64_t)kTilePts;
+        const uint64_t rem = sg->n_points - p0;
+        const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
+        const uint32_t bytes = (npts * (uint32_t)R + 15u) & ~15u;  // bulk copies move multiples of 16 bytes
+        st_tile[s] = tile;
+        st_segi[s] = seg;
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_copy_g2s_hint(dsm + (size_t)s * kTileBytes, sg->rec + p0 * (uint64_t)R, bytes, &full_bar[s], stream_policy);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  GridQEntry* const wq = reinterpret_cast<GridQEntry*>(dsm + (size_t)STAGES * kTileBytes) + (QUEUE ? wid * kGsQCap : 0u);
+  uint32_t qn = 0;  // queued matches of this warp (warp-uniform)
+  uint32_t my_seg = 0xFFFFFFFFu;
+  LaneChunk lch;
+  Segment& S = wseg[wid];
+
+  auto bind_lane = [&]() {
+    if (lch.lane != S.lane) {  // a warp's chunk belongs to one collector's arena
+      if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
+      lch.c = CandChunk();
+      lch.lane = S.lane;
+    }
+  };
+  // insert queued matches, newest first, kGsQFlush at a time (`all`: until the queue is empty)
+  auto flush = [&](bool all) {
+    if constexpr (QUEUE) {
+      __syncwarp();
+      while (qn >= (all ? 1u : kGsQFlush)) {
+        const uint32_t take = qn < kGsQFlush ? qn : kGsQFlush;
+        const uint32_t base = qn - take;
+        bool m[kPPT];
+        QueueFetch f;
+#pragma unroll
+        for (int j = 0; j < kPPT; ++j) {
+          const uint32_t e = (uint32_t)j * 32u + ln;
+          m[j] = e < take;
+          f.qe[j] = wq + base + (m[j] ? e : 0u);
+        }
+        bind_lane();
+        grid_insert_tile(P.lanes[S.lane].grid, S, m, f, lch.c);
+        __syncwarp();
+        qn = base;
+      }
+    }
+  };
+
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t s = it % STAGES;
+    mbar_wait(&full_bar[s], (it / STAGES) & 1u);
+    const unsigned long long tile = st_tile[s];
+    if (tile == ~0ull) break;
+    const uint32_t seg_now = st_segi[s];
+    if (seg_now != my_seg) {
+      if (my_seg != 0xFFFFFFFFu) flush(true);  // queued points belong to the old segment
+      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(&st_seg[s]);
+      uint32_t* dstw = reinterpret_cast<uint32_t*>(&S);
+      for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+      my_seg = seg_now;
+      __syncwarp();
+    }
+    const uint64_t p0 = (tile - S.first_tile) * (uint64_t)kTilePts;
+    const uint64_t rem = S.n_points - p0;
+    const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
+    SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
+    RegFetch f;
+    bool m[kPPT];
+#pragma unroll
+    for (int j = 0; j < kPPT; ++j) {
+      const uint32_t i = wid * 64u + (uint32_t)j * 32u + ln;
+      m[j] = false;
+      Hit h;
+      h.x = h.y = h.z = 0;
+      h.cls = 0;
+      if (i < npts) m[j] = src.template eval<true>(S, P.query_kind, P.cls, p0 + i, i, h);
+      uint32_t rgb[3] = {0u, 0u, 0u};
+      if (m[j]) src.colour(S, p0 + i, i, rgb);
+      f.x[j] = h.x;
+      f.y[j] = h.y;
+      f.z[j] = h.z;
+      f.rg[j] = (rgb[0] & 0xFFFFu) | (rgb[1] << 16);
+      f.bc[j] = (rgb[2] & 0xFFFFu) | ((h.cls & 0xFFu) << 16);
+      f.gi[j] = S.scan_base + p0 + i;
+    }
+    __syncwarp();
+    if (ln == 0) mbar_arrive(&empty_bar[s]);  // the stage may be refilled: everything this warp needs is in registers
+
+    if constexpr (QUEUE) {
+#pragma unroll
+      for (int j = 0; j < kPPT; ++j) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, m[j]);
+        if (m[j]) {
+          GridQEntry& e = wq[qn + (uint32_t)__popc(bal & ((1u << ln) - 1u))];
+          e.x = f.x[j];
+          e.y = f.y[j];
+          e.z = f.z[j];
+          e.rg = f.rg[j];
+          e.bc = f.bc[j];
+          e.gidx = f.gi[j];
+        }
+        qn += (uint32_t)__popc(bal);
+      }
+      flush(false);
+    } else {
+      bind_lane();
+      grid_insert_tile(P.lanes[S.lane].grid, S, m, f, lch.c);
+    }
+  }
+  if (my_seg != 0xFFFFFFFFu) flush(true);
+  if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
+}
+
+// ------------------------------------------------------------------------------------------------
 // MODE_SELECT — BufferCollector::collect_one in scan order (collect_points.rs:29-31): single-pass
 // stable stream compaction with a decoupled look-back prefix.
 //
@@ -985,23 +1268,6 @@ struct SelUnit {
   uint32_t acc;  // consumers: sum of posted warp counts | number of posted warps << 24
   uint32_t warp_cnt[16];  // one per consumer warp (8 in k_select / k_select_bytes, 16 in k_select_ring)
 };
-
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0u;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // L2 cache policies.  The select kernel reads every record once from HBM (`keep`: evict_last) and re-reads the
 // matching ones from L2 a few microseconds later when it emits them (`drop`: evict_first, like the output stores),
@@ -1158,14 +1424,17 @@ __device__ __forceinline__ void select_flush(uint8_t* out, const uint8_t* stage,
 // Emit the matches of consumer warp `w` in unit U (all 32 lanes call it).  index_of(r) is the index, within the
 // warp's `warp_pts` consecutive records of the unit, of the warp's r-th match.  Dense: lane l composes matches l and
 // l + 32 of each round of 64.
+// [r_begin, r_begin + r_count) restricts the call to a range of the warp's matches (index_of takes the full rank).
 template <int AL, class IndexOf>
-__device__ __forceinline__ void select_emit_warp(const SelUnit& U, const IndexOf& index_of, uint32_t warp_pts, uint8_t* stage) {
+__device__ __forceinline__ void select_emit_warp(const SelUnit& U, const IndexOf& index_of_full, uint32_t warp_pts, uint8_t* stage,
+                                                 uint32_t r_begin = 0u, uint32_t r_count = 0xFFFFFFFFu) {
   const uint32_t w = warp_id(), ln = lane_id();
-  const uint32_t mine = U.warp_cnt[w];
+  const uint32_t mine = r_count == 0xFFFFFFFFu ? U.warp_cnt[w] : r_count;
   if (mine == 0) return;
-  uint32_t before = 0;
+  uint32_t before = r_begin;
   for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
   const unsigned long long out0 = U.out_rec + before;
+  auto index_of = [&](uint32_t r) -> uint32_t { return index_of_full(r_begin + r); };
   const Segment& S = U.seg;
   const uint64_t wbase = U.u0 + (uint64_t)w * warp_pts;
   const uint64_t pol = l2_policy_drop();
@@ -1264,6 +1533,19 @@ __device__ __forceinline__ void select_lookback_warp(const ScanParams& P, SelUni
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     // (the unit's aggregate was published by the consumer warp that posted the last count)
+    if (total == 0u && tile != lane_first && !PCQ_HOOK(P, 1u)) {
+      // Nothing to emit, so the unit needs no output slot and nobody has to wait for its prefix: successors look
+      // straight through its (zero) aggregate.  A query without matches would otherwise run at the rate at which the
+      // GPU resolves look-backs instead of at memory speed.  So that later units do not have to walk back over long
+      // runs of such units, the prefix is still published when the predecessor already carries one (one read).
+      if (ln == 0) {
+        const unsigned long long pv = ld_state(P.tile_state + (tile - 1) * kDescStride);
+        if ((pv >> kStatusShift) == kStPrefix) st_state(P.tile_state + tile * kDescStride, pv);  // same prefix: nothing added
+        U.out_rec = U.out_base;
+        mbar_arrive(&bar_pre[b]);
+      }
+      continue;
+    }
     unsigned long long excl = 0;
     if (tile != lane_first && !PCQ_HOOK(P, 1u)) excl = lookback_exclusive(P.tile_state, tile, lane_first);
     if (ln == 0) {
@@ -1617,7 +1899,12 @@ constexpr int kSelBLag = 2;
 constexpr int kSelBDenseRecs = 128;
 constexpr int kSelBStageBytes = 4096;                                    // 128 * 31 + 15 phase bytes, rounded up
 constexpr int kSelBGatherBytes = kSelBDenseRecs * 12;                    // positions of one round
-constexpr int kSelBWarpSmem = kSelBStageBytes + 2 * kSelBGatherBytes;    // per consumer warp (dynamic)
+constexpr int kSelBSearchMax = 512;                                      // up to this many matches per warp-unit: binary search, no list
+constexpr int kSelBListPts = 512;                                        // matches per part of the emit (one full row always fits)
+// (1 KB of list per warp keeps the CTA at 92 KB: two CTAs per SM leave the L1 the 60 KB it had — a 2 KB list pushed the
+// carve-out to 228 KB and the sparse gathers, which live on L1 hits for the second and third word of a position,
+// went from 0.45 to 0.61 ms on 326 M points)
+constexpr int kSelBWarpSmem = kSelBStageBytes + 2 * kSelBGatherBytes + kSelBListPts * 2;  // per consumer warp (dynamic)
 static_assert(kSelBStageBytes >= kSelStageBytes, "the register path stages through the same buffer");
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
@@ -1630,13 +1917,15 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 template <class IndexOf>
-__device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const IndexOf& index_of, uint32_t warp_pts,
-                                                        uint8_t* stage, uint8_t* gbuf, uint32_t cls) {
+__device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const IndexOf& index_of_full, uint32_t warp_pts,
+                                                        uint8_t* stage, uint8_t* gbuf, uint32_t cls, uint32_t r_begin = 0u,
+                                                        uint32_t r_count = 0xFFFFFFFFu) {
   const uint32_t w = warp_id(), ln = lane_id();
-  const uint32_t mine = U.warp_cnt[w];
-  uint32_t before = 0;
+  const uint32_t mine = r_count == 0xFFFFFFFFu ? U.warp_cnt[w] : r_count;
+  uint32_t before = r_begin;
   for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
   const unsigned long long out0 = U.out_rec + before;
+  auto index_of = [&](uint32_t r) -> uint32_t { return index_of_full(r_begin + r); };
   const Segment& S = U.seg;
   const uint64_t wbase = U.u0 + (uint64_t)w * warp_pts;
   const uint64_t pol = l2_policy_drop();
@@ -1697,8 +1986,8 @@ __device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const 
 // unit would be 2 KB and the kernel would run at the unit rate of the look-back machinery, not at memory speed.
 // Same roles and barriers as k_select, but a unit is 32768 points: every consumer warp owns 4096 consecutive class
 // bytes as 8 rows of 32 lanes x 16 bytes (one 16-byte load per lane and row, SIMD byte compare).  Instead of an index
-// list the warp keeps, per lane and row, the 16-bit match mask and the number of matches before it; the emit finds
-// its r-th match with a binary search over those 256 prefixes and a find-nth-set-bit.
+// list the warp keeps, per lane and row, the 16-bit match mask and the number of matches before it; the emit expands
+// them into an index list, half a warp-unit at a time (see below).
 // ------------------------------------------------------------------------------------------------
 
 template <int AL>
@@ -1752,22 +2041,34 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
       uint16_t* mk = m_mask[w][n % (uint32_t)(kSelBLag + 1)];
       uint16_t* pr = m_pre[w][n % (uint32_t)(kSelBLag + 1)];
       uint32_t cnt = 0;
+      uint32_t m16s[kSelBRows];
+      uint32_t any_bits = 0u;
 #pragma unroll
       for (int k = 0; k < kSelBRows; ++k) {
         const uint32_t gi = w * kSelBWarpPts + (uint32_t)k * 512u + ln * 16u;
         uint32_t m16 = nibble(v[k].x) | (nibble(v[k].y) << 4) | (nibble(v[k].z) << 8) | (nibble(v[k].w) << 12);
         const uint32_t valid = gi < npts ? min(16u, npts - gi) : 0u;
         m16 &= (1u << valid) - 1u;
-        const uint32_t c = (uint32_t)__popc(m16);
-        uint32_t incl = c;
+        m16s[k] = m16;
+        any_bits |= m16;
+      }
+      // a warp without a single match in its 4096 bytes (every warp of a class that does not occur) posts zero and is
+      // done: no prefix scans, no mask / prefix stores — its emit is skipped on warp_cnt == 0
+      if (__any_sync(0xffffffffu, any_bits != 0u)) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (ln >= (uint32_t)o) incl += t;
+        for (int k = 0; k < kSelBRows; ++k) {
+          const uint32_t m16 = m16s[k];
+          const uint32_t c = (uint32_t)__popc(m16);
+          uint32_t incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln >= (uint32_t)o) incl += t;
+          }
+          mk[k * 32 + ln] = (uint16_t)m16;
+          pr[k * 32 + ln] = (uint16_t)(cnt + incl - c);
+          cnt += __shfl_sync(0xffffffffu, incl, 31);
         }
-        mk[k * 32 + ln] = (uint16_t)m16;
-        pr[k * 32 + ln] = (uint16_t)(cnt + incl - c);
-        cnt += __shfl_sync(0xffffffffu, incl, 31);
       }
       __syncwarp();
       if (ln == 0) select_post_count(P, U, cnt, &bar_cnt[b]);
@@ -1788,22 +2089,65 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
       if (!PCQ_HOOK(P, 2u)) {
         const uint16_t* mk = m_mask[w][emit_next % (uint32_t)(kSelBLag + 1)];
         const uint16_t* pr = m_pre[w][emit_next % (uint32_t)(kSelBLag + 1)];
-        auto index_of = [mk, pr](uint32_t r) -> uint32_t {
-          uint32_t lo = 0, hi = (uint32_t)kSelBRows * 32u;  // first entry whose prefix exceeds r
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ((uint32_t)pr[mid] > r) hi = mid; else lo = mid + 1u;
-          }
-          const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
-          return e * 16u + nth_set_bit((uint32_t)mk[e], r - (uint32_t)pr[e]);
-        };
         uint8_t* stage_w = selb_dsm + (size_t)w * kSelBWarpSmem;
+        uint16_t* list = reinterpret_cast<uint16_t*>(stage_w + kSelBStageBytes + 2 * kSelBGatherBytes);
         const SelUnit& EU = unit[pb];
+        const uint32_t mine = EU.warp_cnt[w];
         const bool plain = AL == 4 && EU.seg.rgb == nullptr;
-        if (plain && EU.warp_cnt[w] > (uint32_t)kSelBDenseRecs)
-          select_emit_warp_gather(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu);
-        else
-          select_emit_warp<AL>(EU, index_of, (uint32_t)kSelBWarpPts, stage_w);
+        // The warp's matches are emitted in parts of at most kSelBListPts matches (whole rows of its 4096 bytes).  For each part the
+        // index of every match is first written to a list — the owner of a (row, lane) entry walks the set bits of
+        // its 16-bit mask and drops them at the entry's prefix, 32 matches per step of the warp — so that the emit
+        // finds its r-th match with ONE shared-memory load (a binary search over the 256 prefixes per record was a
+        // quarter of this kernel).
+        // (a part = as many whole rows as fit the list: the whole warp-unit when matches are sparse, so that the
+        // rounds of the emit stay as full as they can be)
+        auto pre_at_row = [&](uint32_t row) -> uint32_t { return row < (uint32_t)kSelBRows ? (uint32_t)pr[row * 32u] : mine; };
+        if (mine != 0u && mine <= (uint32_t)kSelBSearchMax) {
+          // few matches (a rare class): the list would cost a pass over all 256 entries for a handful of records;
+          // each lane finds its matches with a binary search over the prefixes instead
+          auto index_of = [mk, pr](uint32_t r) -> uint32_t {
+            uint32_t lo = 0, hi = (uint32_t)kSelBRows * 32u;  // first entry whose prefix exceeds r
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if ((uint32_t)pr[mid] > r) hi = mid; else lo = mid + 1u;
+            }
+            const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
+            return e * 16u + nth_set_bit((uint32_t)mk[e], r - (uint32_t)pr[e]);
+          };
+          if (plain && mine > (uint32_t)kSelBDenseRecs)
+            select_emit_warp_gather(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu);
+          else
+            select_emit_warp<AL>(EU, index_of, (uint32_t)kSelBWarpPts, stage_w);
+          __syncwarp();
+        }
+        for (uint32_t row0 = 0; row0 < (uint32_t)kSelBRows && mine > (uint32_t)kSelBSearchMax;) {
+          const uint32_t r_begin = pre_at_row(row0);
+          uint32_t row1 = row0 + 1u;
+          while (row1 < (uint32_t)kSelBRows && pre_at_row(row1 + 1u) - r_begin <= (uint32_t)kSelBListPts) ++row1;
+          const uint32_t r_count = pre_at_row(row1) - r_begin;
+          const uint32_t rows_lo = row0, rows_hi = row1;
+          row0 = row1;
+          if (r_count == 0u) continue;
+          for (uint32_t row = rows_lo; row < rows_hi; ++row) {
+            const uint32_t e = row * 32u + ln;
+            uint32_t m = mk[e];
+            uint32_t pos = (uint32_t)pr[e] - r_begin;
+            while (__any_sync(0xffffffffu, m != 0u)) {
+              if (m != 0u) {
+                const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                list[pos++] = (uint16_t)(e * 16u + bit);
+              }
+            }
+          }
+          __syncwarp();
+          auto index_of = [list, r_begin](uint32_t r) -> uint32_t { return (uint32_t)list[r - r_begin]; };
+          if (plain && r_count > (uint32_t)kSelBDenseRecs)
+            select_emit_warp_gather(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu, r_begin, r_count);
+          else
+            select_emit_warp<AL>(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, r_begin, r_count);
+          __syncwarp();
+        }
       }
       __syncwarp();
       if (ln == 0) mbar_arrive(&bar_free[pb]);
@@ -2084,6 +2428,41 @@ static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   return check_launch();
 }
 
+template <int R, bool QUEUE>
+static int launch_grid_scan_t(const ScanParams& p, int sm_count, cudaStream_t st) {
+  // dense inserts are bound by the number of resident warps (registers: three CTAs per SM), and a fourth stage costs
+  // a CTA (measured at navvis-XL: 1.43 ms with three stages, 1.96 ms with four); the queue variant runs two CTAs per
+  // SM anyway and gains from the deeper ring (navvis-L: 0.44 vs 0.48 ms)
+  constexpr int STAGES = QUEUE ? (R <= 12 ? 8 : (R <= 20 ? 6 : 4)) : (R <= 12 ? 6 : (R <= 20 ? 4 : 3));
+  constexpr size_t smem = (size_t)STAGES * kTilePts * R + (QUEUE ? (size_t)kGsWarps * kGsQCap * sizeof(GridQEntry) : 0);
+  static bool configured = false;
+  auto kfn = k_grid_scan<R, STAGES, QUEUE>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kGsThreads, smem) != cudaSuccess) return -1;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > (int)kGridCtasPerSm) per_sm = (int)kGridCtasPerSm;
+  uint64_t grid = (uint64_t)sm_count * (uint64_t)per_sm;  // persistent: every CTA resident at once
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid == 0) return 0;
+  kfn<<<(unsigned)grid, kGsThreads, smem, st>>>(p);
+  return check_launch();
+}
+template <bool QUEUE>
+static int launch_grid_scan_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
+  switch (R) {
+    case 12: return launch_grid_scan_t<12, QUEUE>(p, sm_count, st);
+    case 20: return launch_grid_scan_t<20, QUEUE>(p, sm_count, st);
+    case 26: return launch_grid_scan_t<26, QUEUE>(p, sm_count, st);
+    case 28: return launch_grid_scan_t<28, QUEUE>(p, sm_count, st);
+    case 34: return launch_grid_scan_t<34, QUEUE>(p, sm_count, st);
+    default: return 1;  // not instantiated
+  }
+}
+
 template <int MODE>
 static int launch_staged_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
   switch (R) {
@@ -2195,9 +2574,15 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
   if (variant == 2 && staged_supports(uniform_record_len)) {
     int rc = 1;
     if (mode == MODE_COUNT) rc = launch_staged_r<MODE_COUNT>(p, uniform_record_len, sm_count, st);
-    if (mode == MODE_GRID)
-      rc = p.grid_sparse ? launch_staged_r<MODE_GRIDQ>(p, uniform_record_len, sm_count, st)
-                         : launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
+    if (mode == MODE_GRID) {
+      const char* old_k = std::getenv("PCQ_GRID_KERNEL");  // "staged": the barrier-per-tile kernels (measurement only)
+      if (old_k && std::strcmp(old_k, "staged") == 0)
+        rc = p.grid_sparse ? launch_staged_r<MODE_GRIDQ>(p, uniform_record_len, sm_count, st)
+                           : launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
+      else
+        rc = p.grid_sparse ? launch_grid_scan_r<true>(p, uniform_record_len, sm_count, st)
+                           : launch_grid_scan_r<false>(p, uniform_record_len, sm_count, st);
+    }
     if (rc <= 0) return rc;
   }
   if (mode == MODE_COUNT) return launch_direct_t<MODE_COUNT>(p, sm_count, st);

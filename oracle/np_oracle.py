@@ -230,3 +230,44 @@ class SparseGrid:
         for i, p in enumerate(self.cells.values()):
             out[i] = p
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# FileDumper::dump_points (query/src/dump_points.rs:63-116) — what `-o` writes.  TEST INFRASTRUCTURE ONLY.
+# ---------------------------------------------------------------------------------------------------
+def dump_points_plan(buffers):
+    """The files FileDumper writes for a sequence of point buffers (one per collector, in the order main.rs hands
+    them over): -> list of dicts {index, offset, scale, raw, cls, rgb}.
+
+      :65-67   an empty buffer writes nothing and does NOT consume a file index
+      :68-71   matching_points_{file_index}.las, file_index += 1
+      :74-80   min / max position over the buffer; offset = min position
+      :81-88   extent = max - min; max_extent = its largest component; min_scale = max_extent / i32::MAX;
+               scale = 10 ^ ceil(log10(min_scale)); `if scale < 0.001 { scale = 0.001 }` (a zero extent gives
+               log10(0) = -inf -> 10^-inf = 0 -> clamped; NaN compares false and would stay NaN)
+      :90-106  LAS 1.2, point format 2, the same offset / scale on every axis
+    Record quantisation lives in pasture-io's LASWriter (un-vendored, parity unpinned): assumed to be
+    las-rs' Transform::inverse, round((p - offset) / scale) as i32.
+    """
+    out = []
+    index = 0
+    for pts in buffers:
+        pts = np.asarray(pts, dtype=POINT_DTYPE)
+        if len(pts) == 0:
+            continue
+        pos = pts["pos"].astype(np.float64)
+        mn, mx = pos.min(axis=0), pos.max(axis=0)
+        max_extent = float((mx - mn).max())
+        min_scale = max_extent / 2147483647.0
+        with np.errstate(divide="ignore"):
+            scale = float(np.power(10.0, np.ceil(np.log10(min_scale)))) if min_scale > 0 else 0.0
+        if scale < 0.001:
+            scale = 0.001
+        # f64::round rounds half AWAY from zero (np.rint would round half to even); the quotients are >= 0
+        q = (pos - mn) / scale
+        fl = np.floor(q)
+        raw = np.where(q - fl >= 0.5, fl + 1.0, fl)
+        out.append({"index": index, "offset": mn, "scale": scale, "raw": raw.astype(np.int64).astype(np.int32),
+                    "cls": pts["cls"].copy(), "rgb": pts["rgb"].copy()})
+        index += 1
+    return out

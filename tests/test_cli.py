@@ -99,10 +99,35 @@ def test_cli_matches_oracle(pcq, tmp_path, ext):
         assert (cls == 6).all() and xyz.min() >= 0 and scale[0] == scale[1] == scale[2] >= 0.001
     assert total == int(per_file.sum())
 
-    # the records in the first output file are the oracle's records (positions re-quantised by the writer)
+    # the records of EVERY output file are the oracle's records as the oracle's restatement of FileDumper
+    # (dump_points.rs:63-116, oracle/np_oracle.py dump_points_plan) writes them: offset = min position, one scale for all
+    # axes, raw coordinates, classification and colour of every record in scan order; `k` counts non-empty buffers only
+    from oracle import np_oracle
+
     names = sorted(p.name for p in d.iterdir() if p.suffix == f".{ext}")
-    r = subprocess.run([str(QUERY), "-i", str(d / names[0]), "--class", "6", "--optimized", "-o", str(out)], capture_output=True, text=True)
+    listed = [p.name for p in d.iterdir() if p.suffix == f".{ext}"]  # read_dir order == the CLI's file order
+    buffers = []
+    for name in listed:
+        oc = orc.Collector(orc.COLLECT_BUFFER)
+        orc.search_file(files[names.index(name)], ext, oc, cls=6)
+        buffers.append(oc.points())
+    plan = np_oracle.dump_points_plan(buffers)
+    assert [f"matching_points_{e['index']}.las" for e in plan] == [p.name for p in written]
+    for e, p in zip(plan, written):
+        n, scale, offset, xyz, cls, rgb = _read_las_fmt2(p)
+        assert n == len(e["raw"]) and np.array_equal(scale, [e["scale"]] * 3) and np.array_equal(offset, e["offset"])
+        assert np.array_equal(xyz, e["raw"]) and np.array_equal(cls, e["cls"]) and np.array_equal(rgb, e["rgb"])
+    # an empty first buffer does not consume a file index (dump_points.rs:65-71): class 7 is absent from no tile but rare;
+    # a box that misses tile 0 entirely gives an empty first buffer
+    out3 = tmp_path / "out3"
+    out3.mkdir()
+    r = subprocess.run([str(QUERY), "-i", str(d / names[0]), "--class", "6", "--optimized", "-o", str(out3)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    oc = orc.Collector(orc.COLLECT_BUFFER)
+    orc.search_file(files[0], ext, oc, cls=6)
+    (e,) = np_oracle.dump_points_plan([oc.points()])
+    n, scale, offset, xyz, cls, rgb = _read_las_fmt2(out3 / "matching_points_0.las")
+    assert np.array_equal(xyz, e["raw"]) and np.array_equal(rgb, e["rgb"]) and np.array_equal(offset, e["offset"])
 
     # density, no output: no count line at all (main.rs:137-141 with GridSampledCollector::points() = Some)
     r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", bstr, "--optimized", "--density", "25"], capture_output=True, text=True)
@@ -125,3 +150,38 @@ def test_cli_matches_oracle(pcq, tmp_path, ext):
     # without --optimized the request is refused loudly (Regular stays on the reference)
     r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", bstr], capture_output=True, text=True)
     assert r.returncode == 1 and "Regular" in r.stderr
+
+
+# ---- the experiment harness (tools/run_query_experiments.py <- run_query_experiments.rs:106-380) -----------------------
+def _harness(args, timeout=600):
+    import sys
+
+    return subprocess.run([sys.executable, str(ROOT / "tools" / "run_query_experiments.py"), *args], capture_output=True, text=True, timeout=timeout)
+
+
+LINE = re.compile(r"^[a-z0-9_]+;\d+\.\d{6};\d+\.\d{6};\d+\.\d{6}$")
+
+
+def test_experiment_harness_cpu_arm(tmp_path):
+    """the CPU column alone needs no GPU: datasets, every experiment name of the reference's runner, its line format"""
+    assert (ROOT / "oracle" / "query_ref").exists(), "run __graft_entry__.build()"
+    r = _harness(["--generate", str(tmp_path), "--scale", "0.0001", "--input", str(tmp_path), "--runs", "2", "--arms", "cpu"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ";" in ln]
+    assert all(LINE.match(ln) for ln in lines), lines
+    names = [ln.split(";")[0] for ln in lines]
+    # S / L / XL x full / lod x las / last for three datasets, class building / noclass x las / last for two
+    assert len(names) == 3 * 3 * 2 * 2 + 2 * 2 * 2 and all(n.endswith("_cpu") for n in names)
+    for want in ("navvis3_s_full_las_cpu", "doc_xl_lod_last_cpu", "ca13_l_full_last_cpu", "doc_class_building_las_cpu", "ca13_class_noclass_last_cpu"):
+        assert want in names
+
+
+@pytest.mark.gpu
+def test_experiment_harness_gpu_and_cpu_columns_agree(tmp_path):
+    """both arms, one line each per experiment; the harness itself fails when the two `Found N` lines differ"""
+    r = _harness(["--generate", str(tmp_path), "--scale", "0.0005", "--input", str(tmp_path), "--runs", "2", "--experiment", "2"], timeout=1200)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    lines = [ln for ln in r.stdout.splitlines() if ";" in ln]
+    names = [ln.split(";")[0] for ln in lines]
+    assert all(LINE.match(ln) for ln in lines) and len(names) == 2 * 12
+    assert all(n + "_cpu" in names for n in names if not n.endswith("_cpu"))

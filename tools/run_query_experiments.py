@@ -12,6 +12,11 @@ The reference's datasets are private; `--generate DIR` writes seeded synthetic d
 (`--scale` shrinks them: 1.0 = 56.2 M / 64 x 31.25 M / 64 x 40.75 M points).  The page-cache purge of the
 reference (:8-27, macOS `purge`) is replaced by `--drop-caches` (needs root; off by default).
 
+Every experiment is run twice: with the GPU `query` and — the CPU column, `<name>_cpu` — with `oracle/query_ref`, the
+same command line on the CPU oracle (the reference binary itself cannot be built here).  The two must print the same
+"Found N matching points" line or the run fails.  `--arms gpu` / `--arms cpu` run one of them only (the CPU arm needs no
+GPU); `--gpus N` shards every query over N GPUs of the box (`query --gpus N`).
+
     python tools/run_query_experiments.py --generate /dev/shm/pcq --scale 0.01
     python tools/run_query_experiments.py --input /dev/shm/pcq --experiment 2
 """
@@ -25,7 +30,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 QUERY = ROOT / "adhoc-queries-pointclouds_b200" / "query"
+QUERY_CPU = ROOT / "oracle" / "query_ref"
 EXTS = ["las", "last"]
+ARMS = ["gpu", "cpu"]
+GPUS = 1
 
 
 def generate(root: Path, scale: float):
@@ -58,14 +66,15 @@ def purge(drop: bool):
             pass
 
 
-def run_query(args_list, drop):
+def run_query(binary, args_list, drop):
     purge(drop)
     t0 = time.perf_counter()
-    r = subprocess.run([str(QUERY), *args_list], capture_output=True, text=True)
+    r = subprocess.run([str(binary), *args_list], capture_output=True, text=True)
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(f"Could not execute query. Process exited with {r.returncode}: {r.stderr.strip()}")
-    return dt
+    found = [ln for ln in r.stdout.splitlines() if ln.startswith("Found ")]
+    return dt, (found[0] if found else None)
 
 
 def report(name, times):
@@ -73,6 +82,22 @@ def report(name, times):
     median = statistics.median(times)
     std = statistics.stdev(times) if len(times) > 1 else 0.0
     print(f"{name};{mean:.6f};{median:.6f};{std:.6f}", flush=True)
+
+
+def experiment(name, args_list, runs, drop, gpu):
+    """one experiment on both arms; the arms must agree on what they found"""
+    found = {}
+    for arm in ARMS:
+        if arm == "gpu":
+            extra = ["--gpu", str(gpu)] + (["--gpus", str(GPUS)] if GPUS > 1 else [])
+            res = [run_query(QUERY, args_list + extra, drop) for _ in range(runs)]
+        else:
+            res = [run_query(QUERY_CPU, args_list, drop) for _ in range(runs)]
+        assert len({f for _, f in res}) == 1, f"{name}: runs of the {arm} arm disagree"
+        found[arm] = res[0][1]
+        report(name if arm == "gpu" else f"{name}_cpu", [t for t, _ in res])
+    if len(found) == 2 and found["gpu"] != found["cpu"]:
+        raise RuntimeError(f"{name}: GPU printed {found['gpu']!r}, CPU oracle printed {found['cpu']!r}")
 
 
 def aabb_experiments(root: Path, runs: int, which: int, drop: bool, gpu: int):
@@ -92,11 +117,10 @@ def aabb_experiments(root: Path, runs: int, which: int, drop: bool, gpu: int):
                 if not d.exists():
                     continue
                 b = ";".join(repr(float(v)) for v in (*qmin, *qmax))
-                a = ["-i", str(d), "--bounds", b, "--optimized", "--parallel", "--gpu", str(gpu)]
+                a = ["-i", str(d), "--bounds", b, "--optimized", "--parallel"]
                 if dens is not None:
                     a += ["--density", repr(float(dens))]
-                times = [run_query(a, drop) for _ in range(runs)]
-                report(f"{dataset}_{name}_{'lod' if dens is not None else 'full'}_{ext}", times)
+                experiment(f"{dataset}_{name}_{'lod' if dens is not None else 'full'}_{ext}", a, runs, drop, gpu)
 
 
 def class_experiments(root: Path, runs: int, drop: bool, gpu: int):
@@ -106,9 +130,8 @@ def class_experiments(root: Path, runs: int, drop: bool, gpu: int):
                 d = root / dataset / ext
                 if not d.exists():
                     continue
-                a = ["-i", str(d), "--class", str(klass), "--optimized", "--parallel", "--gpu", str(gpu)]
-                times = [run_query(a, drop) for _ in range(runs)]
-                report(f"{dataset}_class_{cname}_{ext}", times)
+                a = ["-i", str(d), "--class", str(klass), "--optimized", "--parallel"]
+                experiment(f"{dataset}_class_{cname}_{ext}", a, runs, drop, gpu)
 
 
 def main():
@@ -120,7 +143,12 @@ def main():
     ap.add_argument("--scale", type=float, default=0.01)
     ap.add_argument("--drop-caches", action="store_true")
     ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=1, help="shard every query over N GPUs (query --gpus N)")
+    ap.add_argument("--arms", default="gpu,cpu", help="gpu,cpu (default), gpu or cpu")
     a = ap.parse_args()
+    global ARMS, GPUS
+    ARMS = [x for x in a.arms.split(",") if x]
+    GPUS = a.gpus
     if a.generate:
         generate(a.generate, a.scale)
         if not a.input:
