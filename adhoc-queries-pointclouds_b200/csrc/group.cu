@@ -1025,15 +1025,26 @@ int pcq_group_create(const int* devices, uint32_t n_devices, pcq_group** out) {
     cudaGetLastError();
     return fail(PCQ_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
   }
-  if ((int)n_devices > n_dev && !devices) return fail(PCQ_ERR_ARG, "%u GPUs asked for, %d present", n_devices, n_dev);
+  if ((int)n_devices > n_dev && !devices && !std::getenv("PCQ_GROUP_DEVICES"))
+    return fail(PCQ_ERR_ARG, "%u GPUs asked for, %d present", n_devices, n_dev);
   pcq_group* g = new (std::nothrow) pcq_group();
   if (!g) return fail(PCQ_ERR_NOMEM, "out of host memory");
   g->world = n_devices;
   g->one_process = true;
   g->local.resize(n_devices);
   std::vector<int> devs(n_devices);
+  // PCQ_GROUP_DEVICES="0,0,1": which device every member of a default group uses (a box with fewer GPUs than members
+  // lets members share a device; the exchange then travels as peer copies)
+  std::vector<int> env_devs;
+  if (!devices)
+    if (const char* e = std::getenv("PCQ_GROUP_DEVICES"))
+      for (const char* c = e; *c;) {
+        env_devs.push_back(std::atoi(c));
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+      }
   for (uint32_t i = 0; i < n_devices; ++i) {
-    devs[i] = devices ? devices[i] : (int)i;
+    devs[i] = devices ? devices[i] : (i < env_devs.size() ? env_devs[i] : (int)i);
     g->local[i].device = devs[i];
     g->local[i].rank = i;
   }

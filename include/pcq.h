@@ -41,10 +41,12 @@ extern "C" {
  *                PCQ_ERR_GRID    ~ SparseGrid::new's "Too many cells" error (grid_sampling.rs:32-34),
  *                PCQ_ERR_ALIASED ~ no counterpart in the reference.  SparseGrid keys that suffer key aliasing
  *                                  (grid_sampling.rs:62-70 vs 78-82: the result for such a key is a sequential
- *                                  fold in scan order) are replayed exactly on one GPU; the code is returned
- *                                  where that order cannot be honoured: merging such collectors across GPUs
- *                                  (pcq_grid_export_candidates), point ranges fed out of scan order, or a hashed
- *                                  table that must be re-hashed in the launch that meets the aliased key.
+ *                                  fold in scan order) are replayed exactly on one GPU and, by the pcq_group_*
+ *                                  searches, across the GPUs of a box (their points are routed to the key's owner);
+ *                                  the code is returned where that order cannot be honoured: point ranges fed to
+ *                                  one collector out of scan order, a hashed table that must be re-hashed in the
+ *                                  launch that meets the aliased key, or the bare pcq_grid_export_candidates on a
+ *                                  collector that holds such keys.
  * ---------------------------------------------------------------------------------------------- */
 enum pcq_status {
   PCQ_OK = 0,
@@ -369,7 +371,7 @@ int pcq_group_search_host_files(pcq_group* g, const void* const* file_bytes, con
 int pcq_result_counts(pcq_result* r, const uint64_t** counts, uint32_t* n_lanes);
 /* ResultCollector::points of a lane: BUFFER in scan order, GRID in arbitrary order; COUNT: NULL / 0.  With one
  * process per GPU the records are gathered on rank 0 (other ranks get NULL / 0; the counts are known everywhere).
- * Pinned host memory owned by the result.                                                                        */
+ * Pinned host memory that the result borrows from its group: release results before their group.               */
 int pcq_result_points(pcq_result* r, uint32_t lane, const pcq_point** out_points, uint64_t* out_n);
 void pcq_result_release(pcq_result* r);
 

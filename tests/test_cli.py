@@ -185,3 +185,68 @@ def test_experiment_harness_gpu_and_cpu_columns_agree(tmp_path):
     names = [ln.split(";")[0] for ln in lines]
     assert all(LINE.match(ln) for ln in lines) and len(names) == 2 * 12
     assert all(n + "_cpu" in names for n in names if not n.endswith("_cpu"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", ["las", "last"])
+def test_cli_on_a_group_of_gpus(pcq, tmp_path, ext):
+    """`query --gpus N`: files and point ranges shard over N GPUs (pcq_group, one process); stdout lines, counts and
+    written records are those of one GPU and of the oracle — including doc-S --density 25, whose grid aliases."""
+    import torch
+
+    from oracle import np_oracle
+
+    S = pcq.synth
+    d = tmp_path / "data"
+    d.mkdir()
+    files = _dataset(pcq, d, ext)
+    env = dict(**__import__("os").environ)
+    n = 3
+    if torch.cuda.device_count() < n:
+        env["PCQ_GROUP_DEVICES"] = ",".join(str(i % torch.cuda.device_count()) for i in range(n))
+    names = sorted(p.name for p in d.iterdir() if p.suffix == f".{ext}")
+    listed = [p.name for p in d.iterdir() if p.suffix == f".{ext}"]
+    order = [names.index(x) for x in listed]  # the CLI's file order (read_dir)
+    box = S.DOC_L
+    bstr = ";".join(str(v) for v in (*box[0], *box[1]))
+    want = orc.count_parallel(files, [ext] * 4, 4, bounds=box)
+    for flags in (["--parallel"], []):
+        r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", bstr, "--optimized", "--gpus", str(n), *flags], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert f"Found {int(want.sum())} matching points" in r.stdout.splitlines()
+    # select with output, per file: the same files FileDumper's restatement writes
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([str(QUERY), "-i", str(d), "--class", "6", "--optimized", "--parallel", "--gpus", str(n), "-o", str(out)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    buffers = []
+    for k in order:
+        oc = orc.Collector(orc.COLLECT_BUFFER)
+        orc.search_file(files[k], ext, oc, cls=6)
+        buffers.append(oc.points())
+    plan = np_oracle.dump_points_plan(buffers)
+    written = sorted(out.glob("matching_points_*.las"), key=lambda p: int(p.stem.split("_")[-1]))
+    assert len(written) == len(plan)
+    for e, p in zip(plan, written):
+        nrec, scale, offset, xyz, cls, rgb = _read_las_fmt2(p)
+        assert np.array_equal(xyz, e["raw"]) and np.array_equal(cls, e["cls"]) and np.array_equal(rgb, e["rgb"]) and np.array_equal(offset, e["offset"])
+    # doc-S + --density 25 (8 z-cells, inclusive z = 200.00 face: aliased keys), sequential: one grid over all files
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    sb = ";".join(str(v) for v in (*S.DOC_S[0], *S.DOC_S[1]))
+    for gpus, odir in ((1, tmp_path / "o1"), (n, out2)):
+        odir.mkdir(exist_ok=True)
+        r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", sb, "--optimized", "--density", "25", "--gpus", str(gpus), "-o", str(odir)],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+    og = orc.Collector(orc.COLLECT_GRID, S.DOC_S[0], S.DOC_S[1], 25.0)
+    for k in order:
+        orc.search_file(files[k], ext, og, bounds=S.DOC_S)
+    (e,) = np_oracle.dump_points_plan([og.points()]) if og.point_count() else (None,)
+    if e is not None:
+        for odir in (tmp_path / "o1", out2):
+            nrec, scale, offset, xyz, cls, rgb = _read_las_fmt2(odir / "matching_points_0.las")
+            assert nrec == og.point_count() and np.array_equal(offset, e["offset"])
+            got = np.concatenate([xyz, cls[:, None].astype(np.int32), rgb.astype(np.int32)], axis=1)
+            exp = np.concatenate([e["raw"], e["cls"][:, None].astype(np.int32), e["rgb"].astype(np.int32)], axis=1)
+            assert np.array_equal(got[np.lexsort(got.T[::-1])], exp[np.lexsort(exp.T[::-1])])  # HashMap order is arbitrary
