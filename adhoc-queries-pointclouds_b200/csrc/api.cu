@@ -470,11 +470,17 @@ int grid_finalize(pcq_collector* c) {
     return PCQ_OK;
   }
   if (c->final_cap < n + n_replayed) {
+    // (with slack: the number of candidates of the same query varies from run to run with the order in which the
+    // GPU happens to meet the points, and a cudaFree + cudaMalloc of a few hundred megabytes costs 20-40 ms)
     if (c->d_final) cudaFree(c->d_final);
     c->d_final = nullptr;
     c->final_cap = 0;
-    CU(cudaMalloc(&c->d_final, (n + n_replayed) * 31ull + 64));
-    c->final_cap = n + n_replayed;
+    const uint64_t cap = n + n_replayed + (n + n_replayed) / 4 + 4096;
+    if (cudaMalloc(&c->d_final, cap * 31ull + 64) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PCQ_ERR_NOMEM, "cannot allocate %llu bytes of HBM for the density result", (unsigned long long)(cap * 31ull));
+    }
+    c->final_cap = cap;
   }
   uint64_t from_table = 0;
   if (n) {
@@ -1246,6 +1252,45 @@ void pcq_collector_destroy(pcq_collector* c) {
   ctx_unref(c->ctx);
   delete c;
 }
+
+}  // extern "C"
+
+namespace pcq {
+
+__global__ void k_zero_blocks(unsigned long long* const* blocks, uint32_t n, uint32_t words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * words) blocks[i / words][i % words] = 0ull;
+}
+
+// pcq_collector_reset for many COUNT / BUFFER collectors of one context with one upload and one launch (a group
+// search resets one collector per file and query: 192 memsets per step of the benchmark were 0.5 ms of launch overhead)
+int reset_collectors_batched(pcq_ctx* ctx, pcq_collector* const* cols, size_t n) {
+  if (n == 0) return PCQ_OK;
+  RC(use_device(ctx));
+  std::vector<unsigned long long*> ptrs(n);
+  for (size_t i = 0; i < n; ++i) {
+    pcq_collector* c = cols[i];
+    if (c->kind == PCQ_COLLECT_GRID || c->ctx != ctx) return fail(PCQ_ERR_ARG, "batched reset serves count / buffer collectors of one context");
+    ptrs[i] = reinterpret_cast<unsigned long long*>(c->dev);
+    c->scan_total = 0;
+    c->out_len = 0;
+    c->cand_len = 0;
+    c->final_valid = false;
+    c->final_n = 0;
+    c->scan_hi = 0;
+  }
+  void* d_ptrs = nullptr;
+  RC(upload(ctx, ptrs.data(), n * sizeof(void*), &d_ptrs));
+  const uint32_t words = 256 / 8;
+  k_zero_blocks<<<(unsigned)((n * words + 255) / 256), 256, 0, ctx->stream>>>(static_cast<unsigned long long* const*>(d_ptrs), (uint32_t)n, words);
+  if (cudaGetLastError() != cudaSuccess) return fail(PCQ_ERR_CUDA, "k_zero_blocks launch failed");
+  ctx->launches++;
+  return PCQ_OK;
+}
+
+}  // namespace pcq
+
+extern "C" {
 
 int pcq_collector_reset(pcq_collector* c) {
   if (!c) return fail(PCQ_ERR_ARG, "null collector");
@@ -2116,8 +2161,9 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
     if (c->d_export) cudaFree(c->d_export);
     c->d_export = nullptr;
     c->export_cap = 0;
-    CU(cudaMalloc(&c->d_export, std::max<uint64_t>(total, 1) * sizeof(Candidate)));
-    c->export_cap = total;
+    const uint64_t cap = total + total / 4 + 1024;
+    CU(cudaMalloc(&c->d_export, cap * sizeof(Candidate)));
+    c->export_cap = cap;
   }
   CU(cudaMemcpyAsync(ctx->part_scratch + n_parts, cursor.data(), n_parts * sizeof(unsigned long long),
                      cudaMemcpyHostToDevice, ctx->stream));

@@ -398,8 +398,11 @@ int take_collectors(Member& M, int kind, size_t n, const GridParams& gp, std::ve
     pool.push_back(c);
   }
   out.assign(pool.begin(), pool.begin() + n);
-  for (pcq_collector* c : out) RC(pcq_collector_reset(c));
-  return PCQ_OK;
+  if (kind == PCQ_COLLECT_GRID) {
+    for (pcq_collector* c : out) RC(pcq_collector_reset(c));
+    return PCQ_OK;
+  }
+  return reset_collectors_batched(M.ctx, out.data(), out.size());
 }
 
 int ensure_h_counts(Member& M, size_t n) {

@@ -183,6 +183,7 @@ int grid_restore(pcq_collector* c);
 int grow_log(pcq_collector* c, uint64_t need);
 int alias_upload(pcq_collector* c);
 int grid_finalize(pcq_collector* c);
+int reset_collectors_batched(pcq_ctx* ctx, pcq_collector* const* cols, size_t n);
 // the host-staged scan of pcq_search_host_files*; `ranges` (one per file, or nullptr) restricts it to point ranges
 int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,
                       uint32_t n_files, const pcq_query* queries, uint32_t n_queries, pcq_collector* const* collectors,

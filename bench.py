@@ -679,7 +679,9 @@ def density_record(pcq, group, ctx, stream, rank, world, local_rank, dev, max_ov
         matches = group.search(ds, [s], B.COLLECT_COUNT, False)[0].counts()[0]
         times, stats = [], None
         res = None
-        for it in range(4):
+        for it in range(5):
+            if res is not None:
+                res.release()  # (hands its pinned buffer back to the group before the next search needs one)
             barrier()
             t0 = time.perf_counter()
             res = group.search(ds, [s], B.COLLECT_GRID, False, grid=grid)[0]

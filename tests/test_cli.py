@@ -201,7 +201,7 @@ def test_cli_on_a_group_of_gpus(pcq, tmp_path, ext):
     d.mkdir()
     files = _dataset(pcq, d, ext)
     env = dict(**__import__("os").environ)
-    n = 3
+    n = int(env.get("PCQ_CLI_GPUS", "3"))  # (PCQ_CLI_GPUS=8 on an 8-GPU box: `query --gpus 8`)
     if torch.cuda.device_count() < n:
         env["PCQ_GROUP_DEVICES"] = ",".join(str(i % torch.cuda.device_count()) for i in range(n))
     names = sorted(p.name for p in d.iterdir() if p.suffix == f".{ext}")
