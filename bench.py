@@ -101,14 +101,52 @@ def tiles_hit(specs, box) -> list:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons of one GPU while it is under load (B200_PROFILING.md's clocks line), sampled through
+    NVML every 5 ms from a thread (nvidia-smi's shortest period, 100 ms, misses the timed region of an 8-GPU run, which
+    lasts tens of milliseconds); falls back to `nvidia-smi -lms 100`."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
+        self.samples = []  # (sm MHz, reasons bit mask)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
         self.lines = []
 
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons")
+                                             else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -123,6 +161,18 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            sm = sorted(s for s, _ in self.samples)
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
+            reasons = [name for name, bit in self.REASONS if mask & bit]
+            top = sm[len(sm) // 2:]  # the upper half: idle samples at the edges of the window drag the median down
+            return {"sm_mhz": statistics.median(top), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "via": "nvml, 5 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -142,9 +192,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # median of the samples under load (the upper half: idle samples before/after the region drag it down)
         top = sorted(sm)[len(sm) // 2:]
-        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "via": "nvidia-smi, 100 ms"}
 
 
 def hbm_peak():
@@ -439,7 +488,6 @@ def main():
     ev1.record(stream)
     ctx.synchronize()
     barrier()
-    clocks = sampler.stop()
     launches = int(sum_over_ranks(float(group.launch_count - launches0)))
     dt_ms = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = dt_ms / args.steps
@@ -459,6 +507,7 @@ def main():
             r[0].counts()
             ctx.synchronize()
             kernel_ms[qi].append(e0.elapsed_time(e1))
+    clocks = sampler.stop()  # sampled from the start of the timed region to the end of this pass (the GPU is busy throughout)
     avg_ms = [statistics.mean(v) for v in kernel_ms]
     bytes_q = [p * R for p in my_scanned]
     achieved = sum(bytes_q) / (sum(avg_ms) * 1e-3) / 1e9
