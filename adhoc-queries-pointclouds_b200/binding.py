@@ -155,6 +155,7 @@ def _load() -> C.CDLL:
         "pcq_collector_point_count": (C.c_int, [vp, P(u64)]),
         "pcq_collector_points": (C.c_int, [vp, P(vp), P(u64)]),
         "pcq_collector_points_device": (C.c_int, [vp, P(vp), P(u64)]),
+        "pcq_collector_las_records": (C.c_int, [vp, P(C.c_double), P(C.c_double), P(C.c_double), P(vp), P(u64)]),
         "pcq_search_files": (C.c_int, [vp, P(vp), u32, P(Query), P(vp), u32]),
         "pcq_search_host_files": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), P(vp), u32]),
         "pcq_search_host_files_multi": (C.c_int, [vp, P(vp), P(sz), P(C.c_char_p), u32, P(Query), u32, P(vp), u32]),

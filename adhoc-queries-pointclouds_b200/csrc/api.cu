@@ -568,6 +568,7 @@ int alias_slow_path(pcq_ctx* ctx, const std::vector<Segment>& segs, ScanParams P
       RC(upload(ctx, lanes.data(), lanes.size() * sizeof(LaneDev), &d_lanes));
       P.segs = static_cast<const Segment*>(d_segs);
       P.lanes = static_cast<const LaneDev*>(d_lanes);
+      if (P.one_grid) P.grid0 = lanes[0].grid;
       if (launch_scan(variant, MODE_GRID, P, R, min_align, ctx->sm_count, ctx->stream) != 0)
         return fail(PCQ_ERR_CUDA, "scan kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       ctx->launches++;
@@ -740,6 +741,10 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     // uniform record length + 16-byte aligned ranges (staged_ok) and a predicate that lives in the staged records
     P.sel_ring = (mode == MODE_SELECT && variant == 2 && !select_bytes) ? R : 0u;
     P.lanes = static_cast<const LaneDev*>(d_lanes);
+    if (mode == MODE_GRID && n_collectors == 1) {
+      P.one_grid = 1u;
+      P.grid0 = lanes[0].grid;
+    }
     if (mode == MODE_SELECT) {
 #ifdef PCQ_DEBUG_HOOKS
       if (const char* e = std::getenv("PCQ_SELECT_DEBUG")) P.debug = (uint32_t)std::atoi(e);
@@ -1206,7 +1211,13 @@ int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const dou
       g.bmax[i] = gmax[i];
       g.dims_f[i] = (double)c->dims[i];  // `self.dimensions.x as f64`
       g.mask[i] = c->bits[i] >= 64 ? ~0ull : ((1ull << c->bits[i]) - 1ull);
+      g.ext[i] = gmax[i] - gmin[i];
+      g.inv_ext[i] = 1.0 / g.ext[i];
     }
+    g.fast_div = 1u;
+    for (int i = 0; i < 3; ++i)
+      if (!(g.ext[i] >= 0x1p-500 && g.ext[i] <= 0x1p500)) g.fast_div = 0u;  // (also NaN, zero extent)
+    if (const char* e = std::getenv("PCQ_GRID_FAST_DIV")) g.fast_div = std::atoi(e) ? g.fast_div : 0u;
     g.cell_size = cell_size;
     g.shift_y = (uint32_t)c->bits[0];
     g.shift_z = (uint32_t)(c->bits[0] + c->bits[1]);

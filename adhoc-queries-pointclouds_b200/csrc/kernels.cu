@@ -55,11 +55,6 @@ __device__ __forceinline__ bool in_range(int32_t v, int32_t lo, int32_t hi) {
   return (uint32_t)(v - lo) <= (uint32_t)(hi - lo);
 }
 
-// (v as f64 * scale) + offset, las.rs:139-141 — two roundings, never an FMA
-__device__ __forceinline__ double reconstruct(int32_t v, double scale, double offset) {
-  return __dadd_rn(__dmul_rn((double)v, scale), offset);
-}
-
 // global loads of possibly unaligned little-endian fields
 __device__ __forceinline__ int32_t ldg_i32(const uint8_t* p, int align) {
   if (align == 4) return __ldg(reinterpret_cast<const int32_t*>(p));
@@ -522,18 +517,17 @@ __device__ __forceinline__ uint64_t l2_stream_policy() {
 }
 __device__ __forceinline__ unsigned long long ld_table(const unsigned long long* p, uint64_t pol) {
   unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
   return v;
 }
 __device__ __forceinline__ void red_min_table(unsigned long long* p, unsigned long long v, uint64_t pol) {
-  asm volatile("red.relaxed.gpu.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+  asm volatile("red.relaxed.gpu.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol));
 }
 // One whole 32-byte sector per store (sm_100: 256-bit st.global, SASS STG.256): half the store instructions of four
 // 16-byte stores per 64-byte candidate, and no half-written sectors in L2.
 __device__ __forceinline__ void stg_sector_stream(void* p, const uint4& a, const uint4& b, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
-               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol)
-               : "memory");
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol));
 }
 
 // Warp-convergent: every lane calls it; m[j] says whether this lane's j-th point matches.
@@ -542,7 +536,7 @@ __device__ __forceinline__ void stg_sector_stream(void* p, const uint4& a, const
 // fold of :97-102 — always survives); the minimum itself is maintained with a fire-and-forget red.min, so nothing
 // waits for an atomic's round trip.  The kPPT points of a lane are taken through each step together so that their
 // table reads are in flight at the same time.
-template <class Fetch>
+template <class Fetch, int kPPT>
 __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment& S, const bool (&m)[kPPT], const Fetch& f,
                                                  CandChunk& ch) {
   bool any_m = false;
@@ -580,7 +574,7 @@ __device__ __forceinline__ void grid_insert_tile(const GridDev& g, const Segment
       }
     }
   }
-  // both table reads of a lane are in flight together (random accesses into a table far larger than L1)
+  // the table reads of a lane are in flight together (random accesses into a table far larger than L1)
 #pragma unroll
   for (int j = 0; j < kPPT; ++j) {
     seen[j] = 0ull;
@@ -1031,16 +1025,61 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 // QUEUE = true (sparse matches, chosen by the host like MODE_GRIDQ): matching points are appended to a per-warp queue
 // in shared memory (no atomics: the warp is the only writer) and inserted 64 at a time with every lane busy.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGsWarps = kTilePts / 64;           // consumer warps: 64 records of a tile each
-constexpr int kGsThreads = (kGsWarps + 1) * 32;   // + the producer warp
+#ifndef PCQ_GRID_MINB
+#define PCQ_GRID_MINB 3
+#endif
 constexpr uint32_t kGsQFlush = 64;                // insert when a warp has queued this many matches
-constexpr uint32_t kGsQCap = kGsQFlush - 1u + 64u + 1u;  // one more tile always fits
+template <int PPT>
+struct GsShape {
+  static constexpr int kWarpPts = 32 * PPT;               // records of a tile per consumer warp
+  static constexpr int kWarps = kTilePts / kWarpPts;      // consumer warps
+  static constexpr int kThreads = (kWarps + 1) * 32;      // + the producer warp
+  static constexpr uint32_t kQCap = kGsQFlush - 1u + (uint32_t)kWarpPts + 1u;  // one more tile always fits
+};
 
-// the two points of a lane, held in registers (the stage they came from is long gone when they are inserted)
+// Records of a tile (or of any 16-byte aligned run of records) in shared memory, taken out with aligned 32-bit loads
+// and one funnel shift per field: 26- and 34-byte records are only 2-byte aligned, and 16-bit loads + merges were a
+// sixth of the density insert's instructions.
+template <int R>
+struct UnitSrc {
+  static_assert(R % 2 == 0, "record fields must be 2-byte aligned in the unit buffer");
+  const uint8_t* unit;  // shared memory, 16-byte aligned
+  __device__ __forceinline__ const uint32_t* words(uint32_t byte_off) const {
+    return reinterpret_cast<const uint32_t*>(unit + (byte_off & ~3u));
+  }
+  __device__ __forceinline__ void xyz(uint32_t i, int32_t& x, int32_t& y, int32_t& z) const {
+    const uint32_t b = i * (uint32_t)R;
+    const uint32_t* w = words(b);
+    if constexpr (R % 4 == 0) {
+      x = (int32_t)w[0];
+      y = (int32_t)w[1];
+      z = (int32_t)w[2];
+    } else {
+      const uint32_t sh = (b & 2u) * 8u;  // 0 or 16
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      x = (int32_t)__funnelshift_r(w0, w1, sh);
+      y = (int32_t)__funnelshift_r(w1, w2, sh);
+      z = (int32_t)__funnelshift_r(w2, w3, sh);
+    }
+  }
+  // r | g << 16 and b of the colour at (even) byte offset o; reads the aligned word pair that holds bytes o .. o+5
+  __device__ __forceinline__ void rgb(uint32_t o, uint32_t& rg, uint32_t& bl) const {
+    const uint32_t* w = words(o);
+    const uint32_t sh = (o & 2u) * 8u;
+    const uint32_t a = w[0], c = w[1];
+    rg = __funnelshift_r(a, c, sh);
+    bl = (c >> sh) & 0xFFFFu;
+  }
+};
+
+
+// the PPT points of a lane, held in registers (the stage they came from is long gone when they are inserted)
+template <int PPT>
 struct RegFetch {
-  int32_t x[kPPT], y[kPPT], z[kPPT];
-  uint32_t rg[kPPT], bc[kPPT];  // r | g << 16,  b | cls << 16
-  unsigned long long gi[kPPT];
+  static constexpr int N = PPT;
+  int32_t x[PPT], y[PPT], z[PPT];
+  uint32_t rg[PPT], bc[PPT];  // r | g << 16,  b | cls << 16
+  unsigned long long gi0;      // collector-wide scan index of point 0 of this lane; point j is 32 j further on
   __device__ __forceinline__ void xyz(int j, int32_t& vx, int32_t& vy, int32_t& vz) const {
     vx = x[j];
     vy = y[j];
@@ -1055,32 +1094,37 @@ struct RegFetch {
     const uint32_t rgb[3] = {rg[j] & 0xFFFFu, rg[j] >> 16, bc[j] & 0xFFFFu};
     point_words(S, h, rgb, w);
   }
-  __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return gi[j]; }
+  __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return gi0 + 32ull * (unsigned)j; }
 };
 
-template <int R, int STAGES, bool QUEUE>
-__global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanParams P) {
+// PPT: records per lane and tile.  The dense insert takes 4 (four consumer warps per CTA): a lane's four table reads
+// and its four chains of dependent FP64 operations are in flight together; the queue variant takes 2.
+// ONE: the launch has one collector — its grid is read from the kernel parameters (constant-bank operands).
+template <int R, int STAGES, bool QUEUE, int PPT, bool ONE>
+__global__ void __launch_bounds__(GsShape<PPT>::kThreads, QUEUE ? 2 : (PPT == 4 ? 4 : PCQ_GRID_MINB)) k_grid_scan(const __grid_constant__ ScanParams P) {
+  using Sh = GsShape<PPT>;
+  constexpr int kWarps = Sh::kWarps;
   constexpr uint32_t kTileBytes = (uint32_t)kTilePts * (uint32_t)R;
-  extern __shared__ __align__(128) uint8_t dsm[];  // STAGES * kTileBytes [+ kGsWarps * kGsQCap queue entries]
+  extern __shared__ __align__(128) uint8_t dsm[];  // STAGES * kTileBytes [+ kWarps * kQCap queue entries]
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ unsigned long long st_tile[STAGES];
   __shared__ uint32_t st_segi[STAGES];
   __shared__ Segment st_seg[STAGES];
-  __shared__ Segment wseg[kGsWarps];
+  __shared__ Segment wseg[kWarps];
 
   const uint32_t wid = warp_id(), ln = lane_id();
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1u);
-      mbar_init(&empty_bar[s], (uint32_t)kGsWarps);
+      mbar_init(&empty_bar[s], (uint32_t)kWarps);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (wid == (uint32_t)kGsWarps) {
+  if (wid == (uint32_t)kWarps) {
     // ---------------- producer warp ----------------
     uint64_t stream_policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
@@ -1121,15 +1165,16 @@ __global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanPar
   }
 
   // ---------------- consumer warps ----------------
-  GridQEntry* const wq = reinterpret_cast<GridQEntry*>(dsm + (size_t)STAGES * kTileBytes) + (QUEUE ? wid * kGsQCap : 0u);
+  GridQEntry* const wq = reinterpret_cast<GridQEntry*>(dsm + (size_t)STAGES * kTileBytes) + (QUEUE ? wid * Sh::kQCap : 0u);
   uint32_t qn = 0;  // queued matches of this warp (warp-uniform)
   uint32_t my_seg = 0xFFFFFFFFu;
   LaneChunk lch;
   Segment& S = wseg[wid];
+  auto grid_of = [&]() -> const GridDev& { return ONE ? P.grid0 : P.lanes[S.lane].grid; };
 
   auto bind_lane = [&]() {
     if (lch.lane != S.lane) {  // a warp's chunk belongs to one collector's arena
-      if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
+      if (lch.lane != 0xFFFFFFFFu) cand_pad(ONE ? P.grid0 : P.lanes[lch.lane].grid, lch.c);
       lch.c = CandChunk();
       lch.lane = S.lane;
     }
@@ -1150,7 +1195,7 @@ __global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanPar
           f.qe[j] = wq + base + (m[j] ? e : 0u);
         }
         bind_lane();
-        grid_insert_tile(P.lanes[S.lane].grid, S, m, f, lch.c);
+        grid_insert_tile(grid_of(), S, m, f, lch.c);
         __syncwarp();
         qn = base;
       }
@@ -1174,32 +1219,50 @@ __global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanPar
     const uint64_t p0 = (tile - S.first_tile) * (uint64_t)kTilePts;
     const uint64_t rem = S.n_points - p0;
     const uint32_t npts = rem < (uint64_t)kTilePts ? (uint32_t)rem : (uint32_t)kTilePts;
-    SmemSrc<R> src{dsm + (size_t)s * kTileBytes};
-    RegFetch f;
-    bool m[kPPT];
+    const UnitSrc<R> src{dsm + (size_t)s * kTileBytes};
+    const bool las = S.layout == PCQ_LAYOUT_LAS;
+    RegFetch<PPT> f;
+    bool m[PPT];
+    f.gi0 = S.scan_base + p0 + wid * (uint32_t)Sh::kWarpPts + ln;
 #pragma unroll
-    for (int j = 0; j < kPPT; ++j) {
-      const uint32_t i = wid * 64u + (uint32_t)j * 32u + ln;
+    for (int j = 0; j < PPT; ++j) {
+      const uint32_t i = wid * (uint32_t)Sh::kWarpPts + (uint32_t)j * 32u + ln;
+      int32_t x = 0, y = 0, z = 0;
+      uint32_t cls = 0, rg = 0, bl = 0;
       m[j] = false;
-      Hit h;
-      h.x = h.y = h.z = 0;
-      h.cls = 0;
-      if (i < npts) m[j] = src.template eval<true>(S, P.query_kind, P.cls, p0 + i, i, h);
-      uint32_t rgb[3] = {0u, 0u, 0u};
-      if (m[j]) src.colour(S, p0 + i, i, rgb);
-      f.x[j] = h.x;
-      f.y[j] = h.y;
-      f.z[j] = h.z;
-      f.rg[j] = (rgb[0] & 0xFFFFu) | (rgb[1] << 16);
-      f.bc[j] = (rgb[2] & 0xFFFFu) | ((h.cls & 0xFFu) << 16);
-      f.gi[j] = S.scan_base + p0 + i;
+      if (i < npts) {
+        src.xyz(i, x, y, z);
+        // (LAST: only bounds queries come here; their class and colour columns are read from global memory)
+        cls = las ? (uint32_t)src.unit[i * (uint32_t)R + S.cls_off] : 0u;
+        if (P.query_kind == PCQ_QUERY_BOUNDS)
+          m[j] = in_range(x, S.lo[0], S.hi[0]) & in_range(y, S.lo[1], S.hi[1]) & in_range(z, S.lo[2], S.hi[2]);
+        else
+          m[j] = cls == P.cls;
+        if (m[j]) {
+          if (las) {
+            if (S.rgb_off >= 0) src.rgb(i * (uint32_t)R + (uint32_t)S.rgb_off, rg, bl);
+          } else {
+            cls = (uint32_t)__ldg(S.cls + p0 + i);
+            if (S.rgb != nullptr) {
+              const uint8_t* p = S.rgb + (p0 + i) * 6ull;
+              rg = ldg_u16(p) | (ldg_u16(p + 2) << 16);
+              bl = ldg_u16(p + 4);
+            }
+          }
+        }
+      }
+      f.x[j] = x;
+      f.y[j] = y;
+      f.z[j] = z;
+      f.rg[j] = rg;
+      f.bc[j] = (bl & 0xFFFFu) | ((cls & 0xFFu) << 16);
     }
     __syncwarp();
     if (ln == 0) mbar_arrive(&empty_bar[s]);  // the stage may be refilled: everything this warp needs is in registers
 
     if constexpr (QUEUE) {
 #pragma unroll
-      for (int j = 0; j < kPPT; ++j) {
+      for (int j = 0; j < PPT; ++j) {
         const uint32_t bal = __ballot_sync(0xffffffffu, m[j]);
         if (m[j]) {
           GridQEntry& e = wq[qn + (uint32_t)__popc(bal & ((1u << ln) - 1u))];
@@ -1208,18 +1271,18 @@ __global__ void __launch_bounds__(kGsThreads, QUEUE ? 2 : 3) k_grid_scan(ScanPar
           e.z = f.z[j];
           e.rg = f.rg[j];
           e.bc = f.bc[j];
-          e.gidx = f.gi[j];
+          e.gidx = f.gidx(S, j);
         }
         qn += (uint32_t)__popc(bal);
       }
       flush(false);
     } else {
       bind_lane();
-      grid_insert_tile(P.lanes[S.lane].grid, S, m, f, lch.c);
+      grid_insert_tile(grid_of(), S, m, f, lch.c);
     }
   }
   if (my_seg != 0xFFFFFFFFu) flush(true);
-  if (lch.lane != 0xFFFFFFFFu) cand_pad(P.lanes[lch.lane].grid, lch.c);
+  if (lch.lane != 0xFFFFFFFFu) cand_pad(ONE ? P.grid0 : P.lanes[lch.lane].grid, lch.c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1469,20 +1532,94 @@ __device__ __forceinline__ void select_emit_warp(const SelUnit& U, const IndexOf
   }
 }
 
+// ---------------- dispatcher state shared by the select kernels ----------------
+// The dispatcher warp hands a CTA its units.  Every unit used to cost it a chain of dependent round trips to L2 — the
+// ticket atomic, the first tile of the next segment, the segment itself, the collector's buffer.  The atomic of the
+// NEXT ticket is now in flight while the current unit is set up, and the segment and its collector are cached (shared
+// memory / lane 0's registers) until a unit crosses into another segment.
+// Tickets are taken ONE at a time: with batches of two (measured) a CTA counts unit t + 1 a whole unit time after
+// unit t, every look-back that crosses such a pair waits for it, and all selects lost 10-25 %.
+constexpr unsigned long long kSelTicketBatch = 1ull;
+
+struct DispatchCache {
+  Segment seg;                    // the segment of the last unit
+  unsigned long long next_first;  // first tile of the following segment (~0: none)
+};
+
+struct Dispatcher {
+  unsigned long long cur = 0, end = 0;  // tickets in hand: [cur, end)
+  unsigned long long ahead = 0;         // lane 0: base of the batch whose atomic is in flight
+  uint32_t seg_cur = 0xFFFFFFFFu;
+  // lane 0: the collector of the cached segment
+  uint8_t* out = nullptr;
+  unsigned long long out_cap = 0, out_base = 0;
+  unsigned long long* count = nullptr;
+
+  __device__ __forceinline__ void start(const ScanParams& P) {
+    if (lane_id() == 0) ahead = atomicAdd(P.ticket, kSelTicketBatch);
+  }
+  __device__ __forceinline__ unsigned long long next_tile(const ScanParams& P) {
+    if (cur == end) {
+      cur = __shfl_sync(0xffffffffu, ahead, 0);
+      end = cur + kSelTicketBatch;
+      if (lane_id() == 0 && cur < P.n_tiles) ahead = atomicAdd(P.ticket, kSelTicketBatch);
+    }
+    return cur++;
+  }
+  // makes `dc` describe the segment of `tile` (the tiles of a CTA only move forward)
+  __device__ __forceinline__ void locate(const ScanParams& P, DispatchCache& dc, unsigned long long tile) {
+    if (seg_cur != 0xFFFFFFFFu && tile < dc.next_first) return;
+    seg_cur = seg_forward(P, seg_cur == 0xFFFFFFFFu ? 0u : seg_cur, tile);
+    const Segment* sg = P.segs + seg_cur;
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
+    uint32_t* dstw = reinterpret_cast<uint32_t*>(&dc.seg);
+    __syncwarp();
+    for (uint32_t k = lane_id(); k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+    if (lane_id() == 0) {
+      dc.next_first = seg_cur + 1 < P.n_segs ? P.segs[seg_cur + 1].first_tile : ~0ull;
+      const LaneDev* L = P.lanes + sg->lane;
+      out = L->out;
+      out_cap = L->out_cap;
+      out_base = L->out_base;
+      count = L->count;
+    }
+    __syncwarp();
+  }
+  // fills the unit descriptor (all lanes copy the segment, lane 0 the scalars); returns the unit's point count
+  template <int UNIT_PTS>
+  __device__ __forceinline__ uint32_t describe(const DispatchCache& dc, SelUnit& U, unsigned long long tile) {
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(&dc.seg);
+    uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
+    for (uint32_t k = lane_id(); k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+    const uint64_t u0 = (tile - dc.seg.first_tile) * (uint64_t)UNIT_PTS;
+    const uint64_t rem = dc.seg.n_points - u0;
+    const uint32_t npts = rem < (uint64_t)UNIT_PTS ? (uint32_t)rem : (uint32_t)UNIT_PTS;
+    if (lane_id() == 0) {
+      U.tile = tile;
+      U.u0 = u0;
+      U.npts = npts;
+      U.out = out;
+      U.out_cap = out_cap;
+      U.out_base = out_base;
+      U.count = count;
+    }
+    return npts;
+  }
+};
+
 // ---------------- dispatcher warp: tickets and unit descriptors, never blocked by a look-back ----------------
 template <int UNIT_PTS>
-__device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelUnit* unit, uint64_t* bar_tk, uint64_t* bar_free) {
+__device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelUnit* unit, uint64_t* bar_tk, uint64_t* bar_free,
+                                                       DispatchCache& dc) {
   const uint32_t ln = lane_id();
-  uint32_t seg_cur = 0;
+  Dispatcher D;
+  D.start(P);
   uint32_t end_marks = 0;  // every look-back warp needs to meet an end marker
   for (uint32_t n = 0;; ++n) {
     const uint32_t b = n % kSelBufs;
     if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
     unsigned long long tile = ~0ull;
-    if (end_marks == 0u) {
-      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
-    }
+    if (end_marks == 0u) tile = D.next_tile(P);
     SelUnit& U = unit[b];
     if (ln == 0) U.acc = 0u;
     if (tile >= P.n_tiles) {
@@ -1493,23 +1630,8 @@ __device__ __forceinline__ void select_dispatcher_warp(const ScanParams& P, SelU
       if (++end_marks == (uint32_t)kSelLbWarps) break;
       continue;
     }
-    seg_cur = seg_forward(P, seg_cur, tile);
-    const Segment* sg = P.segs + seg_cur;
-    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
-    uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
-    for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
-    if (ln == 0) {
-      const LaneDev* L = P.lanes + sg->lane;
-      const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)UNIT_PTS;
-      const uint64_t rem = sg->n_points - u0;
-      U.tile = tile;
-      U.u0 = u0;
-      U.npts = rem < (uint64_t)UNIT_PTS ? (uint32_t)rem : (uint32_t)UNIT_PTS;
-      U.out = L->out;
-      U.out_cap = L->out_cap;
-      U.out_base = L->out_base;
-      U.count = L->count;
-    }
+    D.locate(P, dc, tile);
+    D.template describe<UNIT_PTS>(dc, U, tile);
     __syncwarp();
     if (ln == 0) mbar_arrive(&bar_tk[b]);
   }
@@ -1594,6 +1716,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
   __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];   // all warp counts posted    (consumers -> look-back warp)
   __shared__ __align__(8) uint64_t bar_pre[kSelBufs];   // exclusive prefix resolved (look-back warp -> consumers)
   __shared__ __align__(8) uint64_t bar_free[kSelBufs];  // unit emitted              (consumers -> dispatcher)
+  __shared__ DispatchCache dcache;
   __shared__ __align__(16) uint8_t stage[kSelWarps][kSelStageBytes];
   __shared__ uint16_t match_list[kSelWarps][kSelLag + 1][kSelWarpPts];  // unit-local index of each warp's r-th match
 
@@ -1601,7 +1724,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(ScanParams P) {
   select_init_barriers(bar_tk, bar_cnt, bar_pre, bar_free);
 
   if (warp_id() == kSelWarps + kSelLbWarps) {
-    select_dispatcher_warp<kSelUnitPts>(P, unit, bar_tk, bar_free);
+    select_dispatcher_warp<kSelUnitPts>(P, unit, bar_tk, bar_free, dcache);
     return;
   }
   if (warp_id() >= kSelWarps) {
@@ -1743,6 +1866,7 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
   __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];
   __shared__ __align__(8) uint64_t bar_pre[kSelBufs];
   __shared__ __align__(8) uint64_t bar_free[kSelBufs];
+  __shared__ DispatchCache dcache;
   __shared__ __align__(8) uint64_t bar_full[RS];   // the unit's records have landed   (bulk copy -> consumers)
   __shared__ __align__(8) uint64_t bar_sfree[RS];  // the slot has been balloted        (consumers -> dispatcher)
   // ballot mask of every (warp, row) of the units that are counted but not emitted yet: 60 bytes per warp and unit
@@ -1765,13 +1889,12 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
 
   if (warp_id() == kSelRWarps + kSelLbWarps) {
     // ---------------- dispatcher warp: tickets, unit descriptors and the bulk copies ----------------
-    uint32_t seg_cur = 0;
+    Dispatcher D;
+    D.start(P);
     for (uint32_t n = 0;; ++n) {
       const uint32_t b = n % kSelBufs;
       if (n >= (uint32_t)kSelBufs) mbar_wait(&bar_free[b], (n / kSelBufs - 1u) & 1u);
-      unsigned long long tile = 0;
-      if (ln == 0) tile = atomicAdd(P.ticket, 1ull);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
+      const unsigned long long tile = D.next_tile(P);
       SelUnit& U = unit[b];
       if (ln == 0) U.acc = 0u;
       if (tile >= P.n_tiles) {
@@ -1781,28 +1904,15 @@ __global__ void __launch_bounds__(kSelRThreads, 1) k_select_ring(ScanParams P) {
         }
         break;
       }
-      seg_cur = seg_forward(P, seg_cur, tile);
-      const Segment* sg = P.segs + seg_cur;
-      const uint32_t* srcw = reinterpret_cast<const uint32_t*>(sg);
-      uint32_t* dstw = reinterpret_cast<uint32_t*>(&U.seg);
-      for (uint32_t k = ln; k < sizeof(Segment) / 4; k += 32u) dstw[k] = srcw[k];
+      D.locate(P, dcache, tile);
+      const uint32_t npts = D.template describe<UNIT>(dcache, U, tile);
       const uint32_t slot = n % (uint32_t)RS;
       if (n >= (uint32_t)RS) mbar_wait(&bar_sfree[slot], (n / (uint32_t)RS - 1u) & 1u);
       if (ln == 0) {
-        const LaneDev* L = P.lanes + sg->lane;
-        const uint64_t u0 = (tile - sg->first_tile) * (uint64_t)UNIT;
-        const uint64_t rem = sg->n_points - u0;
-        const uint32_t npts = rem < (uint64_t)UNIT ? (uint32_t)rem : (uint32_t)UNIT;
-        U.tile = tile;
-        U.u0 = u0;
-        U.npts = npts;
-        U.out = L->out;
-        U.out_cap = L->out_cap;
-        U.out_base = L->out_base;
-        U.count = L->count;
+        const uint64_t u0 = (tile - dcache.seg.first_tile) * (uint64_t)UNIT;
         const uint32_t bytes = (npts * (uint32_t)R + 15u) & ~15u;  // bulk copies move multiples of 16 bytes
         mbar_arrive_expect_tx(&bar_full[slot], bytes);
-        bulk_copy_g2s(ring + (size_t)slot * kSlotBytes, sg->rec + u0 * (uint64_t)R, bytes, &bar_full[slot]);
+        bulk_copy_g2s(ring + (size_t)slot * kSlotBytes, dcache.seg.rec + u0 * (uint64_t)R, bytes, &bar_full[slot]);
       }
       __syncwarp();
       if (ln == 0) mbar_arrive(&bar_tk[b]);
@@ -1899,7 +2009,10 @@ constexpr int kSelBLag = 2;
 constexpr int kSelBDenseRecs = 128;
 constexpr int kSelBStageBytes = 4096;                                    // 128 * 31 + 15 phase bytes, rounded up
 constexpr int kSelBGatherBytes = kSelBDenseRecs * 12;                    // positions of one round
-constexpr int kSelBSearchMax = 512;                                      // up to this many matches per warp-unit: binary search, no list
+#ifndef PCQ_SELB_SEARCH_MAX
+#define PCQ_SELB_SEARCH_MAX 512
+#endif
+constexpr int kSelBSearchMax = PCQ_SELB_SEARCH_MAX;                                      // up to this many matches per warp-unit: binary search, no list
 constexpr int kSelBListPts = 512;                                        // matches per part of the emit (one full row always fits)
 // (1 KB of list per warp keeps the CTA at 92 KB: two CTAs per SM leave the L1 the 60 KB it had — a 2 KB list pushed the
 // carve-out to 228 KB and the sparse gathers, which live on L1 hits for the second and third word of a position,
@@ -1907,6 +2020,7 @@ constexpr int kSelBListPts = 512;                                        // matc
 constexpr int kSelBWarpSmem = kSelBStageBytes + 2 * kSelBGatherBytes + kSelBListPts * 2;  // per consumer warp (dynamic)
 static_assert(kSelBStageBytes >= kSelStageBytes, "the register path stages through the same buffer");
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -1997,6 +2111,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
   __shared__ __align__(8) uint64_t bar_cnt[kSelBufs];
   __shared__ __align__(8) uint64_t bar_pre[kSelBufs];
   __shared__ __align__(8) uint64_t bar_free[kSelBufs];
+  __shared__ DispatchCache dcache;
   extern __shared__ __align__(16) uint8_t selb_dsm[];  // per consumer warp: staging buffer, two gather buffers
   __shared__ uint16_t m_mask[kSelWarps][kSelBLag + 1][kSelBRows * 32];  // match mask of (row, lane)
   __shared__ uint16_t m_pre[kSelWarps][kSelBLag + 1][kSelBRows * 32];   // matches of the warp before (row, lane)
@@ -2004,7 +2119,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
   const uint32_t ln = lane_id();
   select_init_barriers(bar_tk, bar_cnt, bar_pre, bar_free);
   if (warp_id() == kSelWarps + kSelLbWarps) {
-    select_dispatcher_warp<kSelBUnitPts>(P, unit, bar_tk, bar_free);
+    select_dispatcher_warp<kSelBUnitPts>(P, unit, bar_tk, bar_free, dcache);
     return;
   }
   if (warp_id() >= kSelWarps) {
@@ -2016,28 +2131,38 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
   const uint32_t pat = (P.cls & 0xFFu) * 0x01010101u;
   const uint64_t pol_keep = l2_policy_keep();
   uint4 v[kSelBRows];
-  uint32_t npts = 0;
-  auto issue_loads = [&](const SelUnit& U) {
-    npts = U.npts;
-    const uint8_t* col = U.seg.cls + U.u0 + (uint64_t)w * kSelBWarpPts;
-#pragma unroll
-    for (int k = 0; k < kSelBRows; ++k) {
-      const uint32_t i = (uint32_t)k * 512u + ln * 16u;
-      v[k] = make_uint4(0u, 0u, 0u, 0u);
-      // a partly valid 16-byte group is still loadable: columns are followed by other columns or by padding
-      if (w * kSelBWarpPts + i < npts) v[k] = ldg_v4_h(col + i, pol_keep);
-    }
+  uint32_t npts = 0;  // points of the unit whose class bytes are in (or on their way into) v
+  auto load_row = [&](const uint8_t* col, uint32_t n_unit, int k) {
+    const uint32_t i = (uint32_t)k * 512u + ln * 16u;
+    v[k] = make_uint4(0u, 0u, 0u, 0u);
+    // a partly valid 16-byte group is still loadable: columns are followed by other columns or by padding
+    if (w * kSelBWarpPts + i < n_unit) v[k] = ldg_v4_h(col + i, pol_keep);
   };
   auto nibble = [&](uint32_t wd) -> uint32_t { return ((__vcmpeq4(wd, pat) & 0x08040201u) * 0x01010101u) >> 24; };
 
   mbar_wait(&bar_tk[0], 0u);
   bool cur = unit[0].tile != ~0ull;
-  if (cur) issue_loads(unit[0]);
+  if (cur) {
+    npts = unit[0].npts;
+    const uint8_t* col = unit[0].seg.cls + unit[0].u0 + (uint64_t)w * kSelBWarpPts;
+#pragma unroll
+    for (int k = 0; k < kSelBRows; ++k) load_row(col, npts, k);
+  }
   uint32_t emit_next = 0;
   for (uint32_t n = 0;; ++n) {
     const uint32_t b = n % kSelBufs;
+    bool nxt = false;
     if (cur) {
       SelUnit& U = unit[b];
+      // The next unit's class bytes are requested row by row, each as soon as the row it replaces has been turned
+      // into its match mask: seven of a lane's eight 16-byte loads stay in flight at all times.  (Requesting the whole
+      // next unit only after this one had been counted left a warp without a byte in flight for half of its time:
+      // a select of a class that does not occur ran at 3.5 TB/s where the count of the same column reaches 6.)
+      const uint32_t nb = (n + 1u) % kSelBufs;
+      mbar_wait(&bar_tk[nb], ((n + 1u) / kSelBufs) & 1u);
+      nxt = unit[nb].tile != ~0ull;
+      const uint32_t npts_next = nxt ? unit[nb].npts : 0u;
+      const uint8_t* ncol = unit[nb].seg.cls + unit[nb].u0 + (uint64_t)w * kSelBWarpPts;  // (only used when nxt)
       uint16_t* mk = m_mask[w][n % (uint32_t)(kSelBLag + 1)];
       uint16_t* pr = m_pre[w][n % (uint32_t)(kSelBLag + 1)];
       uint32_t cnt = 0;
@@ -2051,6 +2176,18 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
         m16 &= (1u << valid) - 1u;
         m16s[k] = m16;
         any_bits |= m16;
+        if (nxt) load_row(ncol, npts_next, k);
+      }
+      npts = npts_next;
+      // ... and the class bytes of the unit after that are asked into L2 (one 128-byte line per lane), if the
+      // dispatcher has described it already: a warp's eight loads are issued back to back and return together, so
+      // without this a warp has 4 KB in flight for one DRAM latency per unit and nothing while it counts.
+      if (nxt) {
+        const uint32_t nb2 = (n + 2u) % kSelBufs;
+        if (mbar_test(&bar_tk[nb2], ((n + 2u) / kSelBufs) & 1u) && unit[nb2].tile != ~0ull) {
+          const uint32_t off = w * (uint32_t)kSelBWarpPts + ln * 128u;
+          if (off < unit[nb2].npts) prefetch_l2(unit[nb2].seg.cls + unit[nb2].u0 + off);
+        }
       }
       // a warp without a single match in its 4096 bytes (every warp of a class that does not occur) posts zero and is
       // done: no prefix scans, no mask / prefix stores — its emit is skipped on warp_cnt == 0
@@ -2074,13 +2211,6 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
       if (ln == 0) select_post_count(P, U, cnt, &bar_cnt[b]);
     }
     const uint32_t counted = cur ? n + 1u : n;
-    bool nxt = false;
-    if (cur) {
-      const uint32_t nb = (n + 1u) % kSelBufs;
-      mbar_wait(&bar_tk[nb], ((n + 1u) / kSelBufs) & 1u);
-      nxt = unit[nb].tile != ~0ull;
-      if (nxt) issue_loads(unit[nb]);
-    }
     while (emit_next < counted) {
       const uint32_t pb = emit_next % kSelBufs;
       const uint32_t par = (emit_next / kSelBufs) & 1u;
@@ -2446,39 +2576,53 @@ static int launch_staged_t(const ScanParams& p, int sm_count, cudaStream_t st) {
   return check_launch();
 }
 
-template <int R, bool QUEUE>
+template <int R, bool QUEUE, int PPT, bool ONE>
 static int launch_grid_scan_t(const ScanParams& p, int sm_count, cudaStream_t st) {
-  // dense inserts are bound by the number of resident warps (registers: three CTAs per SM), and a fourth stage costs
-  // a CTA (measured at navvis-XL: 1.43 ms with three stages, 1.96 ms with four); the queue variant runs two CTAs per
-  // SM anyway and gains from the deeper ring (navvis-L: 0.44 vs 0.48 ms)
+  // dense inserts are bound by the table reads in flight (registers, resident warps), and a fourth stage costs a CTA
+  // (navvis-XL, two records per lane: 1.43 ms with three stages, 1.96 ms with four); the queue variant runs two CTAs
+  // per SM anyway and gains from the deeper ring (navvis-L: 0.44 vs 0.48 ms)
+  using Sh = GsShape<PPT>;
   constexpr int STAGES = QUEUE ? (R <= 12 ? 8 : (R <= 20 ? 6 : 4)) : (R <= 12 ? 6 : (R <= 20 ? 4 : 3));
-  constexpr size_t smem = (size_t)STAGES * kTilePts * R + (QUEUE ? (size_t)kGsWarps * kGsQCap * sizeof(GridQEntry) : 0);
+  constexpr size_t smem = (size_t)STAGES * kTilePts * R + (QUEUE ? (size_t)Sh::kWarps * Sh::kQCap * sizeof(GridQEntry) : 0);
   static bool configured = false;
-  auto kfn = k_grid_scan<R, STAGES, QUEUE>;
+  auto kfn = k_grid_scan<R, STAGES, QUEUE, PPT, ONE>;
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
   }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kGsThreads, smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Sh::kThreads, smem) != cudaSuccess) return -1;
+  if (std::getenv("PCQ_VERBOSE"))
+    std::fprintf(stderr, "k_grid_scan<%d,%d,%d,%d,%d>: %d CTAs per SM, %zu bytes dynamic shared memory\n", R, STAGES, (int)QUEUE, PPT, (int)ONE, per_sm, smem);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > (int)kGridCtasPerSm) per_sm = (int)kGridCtasPerSm;
   uint64_t grid = (uint64_t)sm_count * (uint64_t)per_sm;  // persistent: every CTA resident at once
   if (grid > p.n_tiles) grid = p.n_tiles;
   if (grid == 0) return 0;
-  kfn<<<(unsigned)grid, kGsThreads, smem, st>>>(p);
+  kfn<<<(unsigned)grid, Sh::kThreads, smem, st>>>(p);
   return check_launch();
 }
-template <bool QUEUE>
+template <bool QUEUE, int PPT, bool ONE>
 static int launch_grid_scan_r(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
   switch (R) {
-    case 12: return launch_grid_scan_t<12, QUEUE>(p, sm_count, st);
-    case 20: return launch_grid_scan_t<20, QUEUE>(p, sm_count, st);
-    case 26: return launch_grid_scan_t<26, QUEUE>(p, sm_count, st);
-    case 28: return launch_grid_scan_t<28, QUEUE>(p, sm_count, st);
-    case 34: return launch_grid_scan_t<34, QUEUE>(p, sm_count, st);
+    case 12: return launch_grid_scan_t<12, QUEUE, PPT, ONE>(p, sm_count, st);
+    case 20: return launch_grid_scan_t<20, QUEUE, PPT, ONE>(p, sm_count, st);
+    case 26: return launch_grid_scan_t<26, QUEUE, PPT, ONE>(p, sm_count, st);
+    case 28: return launch_grid_scan_t<28, QUEUE, PPT, ONE>(p, sm_count, st);
+    case 34: return launch_grid_scan_t<34, QUEUE, PPT, ONE>(p, sm_count, st);
     default: return 1;  // not instantiated
   }
+}
+static int launch_grid_scan(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
+  static const int dense_ppt = [] {
+    const char* e = std::getenv("PCQ_GRID_PPT");  // measurement only
+    return e ? std::atoi(e) : 2;
+  }();
+  if (p.grid_sparse)
+    return p.one_grid ? launch_grid_scan_r<true, 2, true>(p, R, sm_count, st) : launch_grid_scan_r<true, 2, false>(p, R, sm_count, st);
+  if (dense_ppt == 2)
+    return p.one_grid ? launch_grid_scan_r<false, 2, true>(p, R, sm_count, st) : launch_grid_scan_r<false, 2, false>(p, R, sm_count, st);
+  return p.one_grid ? launch_grid_scan_r<false, 4, true>(p, R, sm_count, st) : launch_grid_scan_r<false, 4, false>(p, R, sm_count, st);
 }
 
 template <int MODE>
@@ -2598,8 +2742,7 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
         rc = p.grid_sparse ? launch_staged_r<MODE_GRIDQ>(p, uniform_record_len, sm_count, st)
                            : launch_staged_r<MODE_GRID>(p, uniform_record_len, sm_count, st);
       else
-        rc = p.grid_sparse ? launch_grid_scan_r<true>(p, uniform_record_len, sm_count, st)
-                           : launch_grid_scan_r<false>(p, uniform_record_len, sm_count, st);
+        rc = launch_grid_scan(p, uniform_record_len, sm_count, st);
     }
     if (rc <= 0) return rc;
   }

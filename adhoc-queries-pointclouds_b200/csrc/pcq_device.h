@@ -79,7 +79,9 @@ struct GridDev {
   uint32_t log_only;     // 1: second pass of a launch that met new affected keys — log their points, insert nothing
   uint32_t own_parts;    // finalisation: > 1 = only cells with mix64(key) % own_parts == own_me are finalists (multi-GPU owner)
   uint32_t own_me;
-  uint32_t pad_;
+  uint32_t fast_div;     // 1: every axis extent is a normal number in [2^-500, 2^500] — division by reciprocal (grid_math.cuh)
+  double ext[3];         // bmax - bmin, the divisor of :51-57
+  double inv_ext[3];     // RN(1 / ext), IEEE division on the host
   Candidate* log;        // replay log: {key, -, scan index, point} of every point of an affected key / aliased point
   unsigned long long* log_count;
   uint64_t log_cap;
@@ -135,6 +137,8 @@ struct ScanParams {
   uint32_t grid_sparse;            // MODE_GRID: 1 = few points are expected to match: use the match-queue kernels
   uint32_t sel_bytes;              // MODE_SELECT: 1 = k_select_bytes (LAST class query, 32768-point units)
   uint32_t sel_ring;               // MODE_SELECT: record length when the launch qualifies for k_select_ring, else 0
+  uint32_t one_grid;               // MODE_GRID: 1 = the launch has one collector; its grid is grid0 (constant bank operands)
+  GridDev grid0;
   uint32_t debug;                  // measurement hooks, only in -DPCQ_DEBUG_HOOKS builds: 1 = skip the look-back, 2 = skip the emit
 };
 

@@ -248,32 +248,34 @@ static void put(std::vector<uint8_t>& b, size_t off, T v) {
   std::memcpy(b.data() + off, &v, sizeof(T));
 }
 
-void FileDumper::dump_points(const pcq_point* points, size_t n) {
-  if (n == 0) return;  // :65-67
-  const std::string path = root_ + "/matching_points_" + std::to_string(file_index_) + ".las";
-  file_index_ += 1;
-
-  // :74-88 — offset = min position, one scale for all axes
-  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  for (size_t i = 0; i < n; ++i) {
-    pcq_point p;
-    std::memcpy(&p, points + i, sizeof(p));
-    for (int a = 0; a < 3; ++a) {
-      mn[a] = std::min(mn[a], p.pos[a]);
-      mx[a] = std::max(mx[a], p.pos[a]);
-    }
+bool PointDumper::dump_collector(ResultCollector& collector) {
+  const pcq_point* ref = nullptr;
+  uint64_t n = 0;
+  if (collector.points_ref(&ref, &n)) {
+    dump_points(ref, n);
+    return true;
   }
-  const double max_extent = std::max({mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]});
+  if (auto pts = collector.points()) {
+    dump_points(pts->data(), pts->size());
+    return true;
+  }
+  return false;
+}
+
+static double writer_scale(double max_extent) {
+  // :81-88
   const double min_scale = max_extent / (double)INT32_MAX;
   double scale = std::pow(10.0, std::ceil(std::log10(min_scale)));
   if (!(scale >= 0.001)) scale = 0.001;  // `if scale < 0.001` plus the NaN/0 cases of a zero extent
+  return scale;
+}
 
+void FileDumper::write_file(const double mn[3], const double mx[3], double scale, const uint8_t* records, size_t n) {
+  const std::string path = root_ + "/matching_points_" + std::to_string(file_index_) + ".las";
+  file_index_ += 1;
   std::printf("Writing %zu points\n", n);  // :108
-
-  // Byte-level parity with pasture-io's LASWriter is unpinned (un-vendored crate): raw coordinates use
-  // las-rs' Transform::inverse rule round((p - offset) / scale).
   const size_t rec = 26;
-  std::vector<uint8_t> out(227 + n * rec, 0);
+  std::vector<uint8_t> out(227, 0);
   std::memcpy(out.data(), "LASF", 4);
   out[24] = 1;
   out[25] = 2;
@@ -294,10 +296,36 @@ void FileDumper::dump_points(const pcq_point* points, size_t n) {
     put<double>(out, 179 + 16 * a, mx[a]);
     put<double>(out, 187 + 16 * a, mn[a]);
   }
+  std::ofstream f(path, std::ios::binary);
+  if (!f) throw Error(PCQ_ERR_IO, "cannot create " + path);
+  f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
+  f.write(reinterpret_cast<const char*>(records), (std::streamsize)(n * rec));
+  if (!f) throw Error(PCQ_ERR_IO, "cannot write " + path);
+  dumped_ += n;
+}
+
+// points that are already on the host (a group's result): the per-point work happens here
+void FileDumper::dump_points(const pcq_point* points, size_t n) {
+  if (n == 0) return;  // :65-67
+  // :74-88 — offset = min position, one scale for all axes
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   for (size_t i = 0; i < n; ++i) {
     pcq_point p;
     std::memcpy(&p, points + i, sizeof(p));
-    uint8_t* r = out.data() + 227 + i * rec;
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = std::min(mn[a], p.pos[a]);
+      mx[a] = std::max(mx[a], p.pos[a]);
+    }
+  }
+  const double scale = writer_scale(std::max({mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]}));
+  // Byte-level parity with pasture-io's LASWriter is unpinned (un-vendored crate): raw coordinates use
+  // las-rs' Transform::inverse rule round((p - offset) / scale).
+  const size_t rec = 26;
+  std::vector<uint8_t> out(n * rec, 0);
+  for (size_t i = 0; i < n; ++i) {
+    pcq_point p;
+    std::memcpy(&p, points + i, sizeof(p));
+    uint8_t* r = out.data() + i * rec;
     for (int a = 0; a < 3; ++a) {
       const double q = std::round((p.pos[a] - mn[a]) / scale);
       const int32_t v = q >= 2147483647.0 ? INT32_MAX : (q <= -2147483648.0 ? INT32_MIN : (int32_t)q);
@@ -307,11 +335,18 @@ void FileDumper::dump_points(const pcq_point* points, size_t n) {
     r[15] = p.cls;
     std::memcpy(r + 20, p.rgb, 6);
   }
-  std::ofstream f(path, std::ios::binary);
-  if (!f) throw Error(PCQ_ERR_IO, "cannot create " + path);
-  f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
-  if (!f) throw Error(PCQ_ERR_IO, "cannot write " + path);
-  dumped_ += n;
+  write_file(mn, mx, scale, out.data(), n);
+}
+
+// a collector that lives in HBM: the library reduces and quantises on the device
+bool FileDumper::dump_collector(ResultCollector& collector) {
+  if (collector.kind() == PCQ_COLLECT_COUNT) return false;  // `points()` == None
+  double mn[3], mx[3], scale = 0.0;
+  const uint8_t* records = nullptr;
+  uint64_t n = 0;
+  check(pcq_collector_las_records(collector.handle(), mn, mx, &scale, &records, &n));
+  if (n != 0) write_file(mn, mx, scale, records, (size_t)n);
+  return true;
 }
 
 }  // namespace pcq_host

@@ -63,6 +63,7 @@ class ResultCollector {
   virtual bool points_ref(const pcq_point** out, uint64_t* n);
   size_t point_count();
   pcq_collector* handle() const { return h_; }
+  int kind() const { return kind_; }
 
  protected:
   ResultCollector(Context& ctx, int kind, const AABB* bounds, double cell_size);
@@ -184,11 +185,20 @@ class PointDumper {
   virtual ~PointDumper() = default;
   virtual void dump_points(const pcq_point* points, size_t n) = 0;
   virtual size_t num_dumped_points() const = 0;
+  // what run_search_* do with a finished collector (main.rs:134-143, 165-169): hand its points to dump_points.
+  // Returns false for a CountCollector (`points()` == None).
+  virtual bool dump_collector(ResultCollector& collector);
 };
 
 class IgnoreDumper : public PointDumper {
  public:
   void dump_points(const pcq_point*, size_t n) override { dumped_ += n; }
+  // (counts what it is handed, dump_points.rs:27-30: no point has to leave the device for that)
+  bool dump_collector(ResultCollector& collector) override {
+    if (collector.kind() == PCQ_COLLECT_COUNT) return false;
+    dumped_ += collector.point_count();
+    return true;
+  }
   size_t num_dumped_points() const override { return dumped_; }
 
  private:
@@ -201,9 +211,12 @@ class FileDumper : public PointDumper {
  public:
   explicit FileDumper(const std::string& root_dir);
   void dump_points(const pcq_point* points, size_t n) override;
+  // the same file, with the min / max reduction and the quantisation done on the device (pcq_collector_las_records)
+  bool dump_collector(ResultCollector& collector) override;
   size_t num_dumped_points() const override { return dumped_; }
 
  private:
+  void write_file(const double mn[3], const double mx[3], double scale, const uint8_t* records, size_t n);
   std::string root_;
   size_t file_index_ = 0;
   size_t dumped_ = 0;

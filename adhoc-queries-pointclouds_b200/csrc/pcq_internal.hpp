@@ -183,6 +183,8 @@ int grid_restore(pcq_collector* c);
 int grow_log(pcq_collector* c, uint64_t need);
 int alias_upload(pcq_collector* c);
 int grid_finalize(pcq_collector* c);
+// writer.cu: scale of the -o output (dump_points.rs:81-88)
+double las_writer_scale(double max_extent);
 int reset_collectors_batched(pcq_ctx* ctx, pcq_collector* const* cols, size_t n);
 // the host-staged scan of pcq_search_host_files*; `ranges` (one per file, or nullptr) restricts it to point ranges
 int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t* n_bytes, const char* const* exts,

@@ -65,15 +65,7 @@ void usage() {
 void run_search_sequential(const std::vector<std::string>& files, Searcher& searcher, SearchImplementation impl,
                            ResultCollector& collector, PointDumper& dumper) {
   if (!files.empty()) searcher.search_files(files, impl, {&collector});
-  const pcq_point* ref = nullptr;
-  uint64_t n = 0;
-  if (collector.points_ref(&ref, &n)) {
-    dumper.dump_points(ref, n);
-  } else if (auto pts = collector.points()) {
-    dumper.dump_points(pts->data(), pts->size());
-  } else {
-    std::printf("Found %zu matching points\n", collector.point_count());
-  }
+  if (!dumper.dump_collector(collector)) std::printf("Found %zu matching points\n", collector.point_count());
 }
 
 // run_search_parallel (main.rs:146-183): one collector per file, results consumed in `files` order
@@ -85,13 +77,7 @@ void run_search_parallel(const std::vector<std::string>& files, Searcher& search
   bool have_matches = false;
   size_t num_matches = 0;
   for (auto& c : collectors) {
-    const pcq_point* ref = nullptr;
-    uint64_t n = 0;
-    if (c->points_ref(&ref, &n)) {
-      dumper.dump_points(ref, n);
-    } else if (auto pts = c->points()) {
-      dumper.dump_points(pts->data(), pts->size());
-    } else {
+    if (!dumper.dump_collector(*c)) {
       have_matches = true;
       num_matches += c->point_count();
     }

@@ -183,6 +183,17 @@ class ResultCollector:
     def points_ref(self) -> Optional[np.ndarray]:
         return self.points() if self.kind == B.COLLECT_BUFFER else None
 
+    def las_records(self):
+        """FileDumper's output for this collector (dump_points.rs:63-116), reduced and quantised on the device:
+        -> (offset[3], max[3], scale, records uint8[n, 26]) or None when there is nothing to write."""
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        scale, p, n = C.c_double(), C.c_void_p(), C.c_uint64()
+        check(lib.pcq_collector_las_records(self.handle, mn, mx, C.byref(scale), C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return None
+        raw = (C.c_uint8 * (26 * n.value)).from_address(p.value)
+        return np.array(mn[:]), np.array(mx[:]), float(scale.value), np.frombuffer(raw, dtype=np.uint8).reshape(-1, 26).copy()
+
     def reset(self):
         check(lib.pcq_collector_reset(self.handle))
 

@@ -622,6 +622,10 @@ def main():
     del pieces, bufs
     torch.cuda.empty_cache()
 
+    # ---- e2e sub-value (N = 1): repeated queries over acquisition-ordered tiles with the on-the-fly chunk index ----
+    if e2e is not None and world == 1 and not args.no_extra:
+        e2e["strip_ordered_indexed_repeat"] = e2e_indexed_repeat(pcq, ctx, specs, qs, scanned_pts, R)
+
     # ---- density (C4): one navvis-shape file, range-sharded, bounds + --density 0.1, cell all-to-all ----
     density = None
     if not args.no_density:
@@ -675,6 +679,83 @@ def e2e_last(pcq, group, specs, minmax, bufs, searchers, scanned_pts, hit_files,
     out = {"value": scanned_pts / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_steps,
            "h2d_bytes_per_step": sum(specs[f].n_points for f in files_any) * 12,
            "note": "same points, same queries, same counts; the files are LAST (columnar): a bounds count needs the position column only"}
+    for hi in keep:
+        hi.close()
+    return out
+
+
+def e2e_indexed_repeat(pcq, ctx, specs, qs, scanned_pts, R):
+    """The C2 tiles with their points in ACQUISITION order (every tile = 16 flight strips stored one after the other,
+    each covering its own band of x with 10 % overlap), host-staged through pcq_search_host_files_indexed: the first
+    pass copies everything and builds the chunk headers as a by-product (improvements.md:3-10), every later pass copies
+    only the runs of chunks in which some query of the step can find a match.  Same shape, sizes and queries as the
+    headline workload; the points differ (they are generated strip by strip), so the counts are checked against the
+    unindexed pass over the same images."""
+    import copy
+
+    import torch
+
+    S, B = pcq.synth, pcq.binding
+    n_strips = 16
+    searchers = [pcq.BoundsSearcher(*box) for _, box in qs]
+    dev = f"cuda:{ctx.device}"
+    keep, images = [], []
+    tmp = torch.empty(max(sp.n_points for sp in specs) * R + 256, dtype=torch.uint8, device=dev)
+    for f, sp in enumerate(specs):
+        per = sp.n_points // n_strips
+        w = (sp.hi[0] - sp.lo[0] + 1) // n_strips
+        lo_all, hi_all = [2**31 - 1] * 3, [-(2**31)] * 3
+        for k in range(n_strips):
+            sk = copy.copy(sp)
+            sk.seed = (sp.seed + 7919 * (k + 1)) & 0xFFFFFFFFFFFFFFFF
+            sk.n_points = per if k < n_strips - 1 else sp.n_points - per * (n_strips - 1)
+            sk.lo[0] = max(sp.lo[0], sp.lo[0] + k * w - w // 10)
+            sk.hi[0] = min(sp.hi[0], sp.lo[0] + (k + 1) * w + w // 10)
+            mm, _ = S.device_points(ctx, sk, tmp.data_ptr() + k * per * R)
+            lo_all = [min(a, b) for a, b in zip(lo_all, mm[:3])]
+            hi_all = [max(a, b) for a, b in zip(hi_all, mm[3:])]
+        hi = HostImage(pcq, 227 + sp.n_points * R, S.header_bytes(sp, lo_all + hi_all), 0, sp.n_points * R, tmp)
+        keep.append(hi)
+        images.append(((hi.addr, hi.nbytes), "las"))
+    torch.cuda.synchronize()
+    del tmp
+    torch.cuda.empty_cache()
+
+    def new_cols():
+        return [[pcq.CountCollector(ctx) for _ in specs] for _ in searchers]
+
+    def run(index):
+        cols = new_cols()
+        t0 = time.perf_counter()
+        pcq.search_host_files_multi(images, searchers, cols, index=index)
+        got = [[c.point_count() for c in cs] for cs in cols]
+        dt = time.perf_counter() - t0
+        st = ctx.last_scan_stats()
+        for cs in cols:
+            for c in cs:
+                c.close()
+        return got, dt, st
+
+    want, _, _ = run(None)          # unindexed pass over the same images: the counts to match
+    want2, dt_plain, _ = run(None)
+    assert want2 == want
+    hix = pcq.HostIndex(ctx)
+    got, dt_first, _ = run(hix)     # first indexed pass: copies everything, builds the headers
+    assert got == want, "first (index-building) pass differs from the unindexed pass"
+    dts, st = [], None
+    for _ in range(3):
+        got, dt, st = run(hix)
+        assert got == want, "indexed pass differs from the unindexed pass"
+        dts.append(dt)
+    dt = statistics.median(dts)
+    out = {"value": scanned_pts / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": len(dts),
+           "unindexed_ms_per_step": dt_plain * 1e3, "first_pass_ms": dt_first * 1e3,
+           "matches_per_step": [int(sum(g)) for g in got],
+           "note": "C2 shape with the points of every tile in acquisition order (16 flight strips per tile); "
+                   "pcq_search_host_files_indexed, passes after the first; counts equal the unindexed pass over the same images"}
+    out["h2d_bytes_per_step"] = int(st.points_scanned) * R  # the points of the chunk runs that crossed PCIe
+    out["chunks_skipped"], out["chunks_total"] = int(st.chunks_skipped), int(st.chunks_total)
+    hix.close()
     for hi in keep:
         hi.close()
     return out

@@ -183,6 +183,16 @@ int pcq_collector_point_count(pcq_collector* c, uint64_t* out);
 int pcq_collector_points(pcq_collector* c, const pcq_point** out_points, uint64_t* out_n);
 /* Same records, left in HBM (device pointer, 31-byte stride). */
 int pcq_collector_points_device(pcq_collector* c, const void** out_dev_points, uint64_t* out_n);
+/* The `-o` output of the query (FileDumper::dump_points, dump_points.rs:63-116) prepared on the device: the
+ * collector's points as LAS 1.2 point format 2 records (26 bytes each: x, y, z = round((p - min) / scale) as i32,
+ * return byte 0x09, classification, r, g, b) together with the header values of :74-88 — out_min = offset = smallest
+ * position, out_max, out_scale = max(10^ceil(log10(max_extent / i32::MAX)), 0.001).  A min / max reduction and a
+ * quantisation kernel replace the per-point host loops, and 26 instead of 31 bytes per record cross PCIe.
+ * BUFFER: scan order; GRID: the order of pcq_collector_points.  *out_records is pinned host memory owned by the
+ * collector, valid until the next call on it; *out_n == 0 (nothing to write, :65-67) leaves the other outputs untouched.
+ * COUNT collectors: *out_n = 0. */
+int pcq_collector_las_records(pcq_collector* c, double out_min[3], double out_max[3], double* out_scale,
+                              const uint8_t** out_records, uint64_t* out_n);
 
 /* ---- the scan ---------------------------------------------------------------------------------- */
 

@@ -685,3 +685,37 @@ def test_density_exchange_over_nccl_when_two_gpus(pcq):
                         "--master-port", "29517", os.path.join(root, "tests", "dist_density_nccl.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MISMATCH" not in r.stdout and r.stdout.count("OK") == 4
+
+
+# ---- -o output prepared on the device (pcq_collector_las_records <- dump_points.rs:63-116) -----------------------------
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 70_001])
+def test_las_records_on_device_equal_the_restated_file_dumper(pcq, ctx, n):
+    """The device-side min / max reduction + quantisation writes what the oracle's restatement of FileDumper writes from
+    the oracle's points: offset = min position, scale, raw coordinates, class and colour of every record, in scan order."""
+    from oracle import np_oracle
+
+    rng = np.random.default_rng(700 + n)
+    xyz = rng.integers(-2_000_000, 2_000_000, size=(n, 3), dtype=np.int64).astype(np.int32)
+    cls = rng.integers(0, 4, size=n).astype(np.uint8)
+    rgb = rng.integers(0, 65536, size=(n, 3)).astype(np.uint16)
+    f = make_file(xyz, cls, rgb=rgb, fmt=3, scale=(0.001, 0.001, 0.001), offset=(-23.108, -21.261, -10.029))
+    box = ((-1e9,) * 3, (1e9,) * 3)
+    for kind, kw in ((orc.COLLECT_BUFFER, dict(bounds=box)), (orc.COLLECT_BUFFER, dict(cls=1)),
+                     (orc.COLLECT_GRID, dict(bounds=box, grid=((-2100.0,) * 3, (2100.0,) * 3, 50.0)))):
+        got = gpu_run(pcq, ctx, [f], ["las"], kind, **kw)[0]
+        want = oracle_run([f], ["las"], kind, **kw)[0]
+        res = got.las_records()
+        if want.point_count() == 0:
+            assert res is None
+            continue
+        pts = got.points()  # GRID: the device's own order (HashMap order in the reference); the set is checked elsewhere
+        if kind == orc.COLLECT_BUFFER:
+            assert pts.tobytes() == want.points().tobytes()
+        (e,) = np_oracle.dump_points_plan([pts])
+        mn, mx, scale, rec = res
+        assert np.array_equal(mn, e["offset"]) and scale == e["scale"] and np.array_equal(mx, pts["pos"].max(axis=0))
+        assert rec.shape == (len(pts), 26)
+        assert np.array_equal(np.ascontiguousarray(rec[:, :12]).view("<i4").reshape(-1, 3), e["raw"])
+        assert np.array_equal(rec[:, 15], e["cls"]) and (rec[:, 14] == 0x09).all()
+        assert np.array_equal(np.ascontiguousarray(rec[:, 20:26]).view("<u2").reshape(-1, 3), e["rgb"])
+        assert not rec[:, [12, 13, 16, 17, 18, 19]].any()
