@@ -33,6 +33,7 @@ from .searcher import (  # noqa: F401
     index_filter,
     run_search_parallel,
     run_search_sequential,
+    reset_collectors,
     search_host_files_multi,
     search_las_file_by_bounds_optimized,
     search_las_file_by_classification_optimized,

@@ -152,6 +152,7 @@ def _load() -> C.CDLL:
         "pcq_collector_create": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, P(vp)]),
         "pcq_collector_destroy": (None, [vp]),
         "pcq_collector_reset": (C.c_int, [vp]),
+        "pcq_collectors_reset": (C.c_int, [P(vp), u32]),
         "pcq_collector_point_count": (C.c_int, [vp, P(u64)]),
         "pcq_collector_points": (C.c_int, [vp, P(vp), P(u64)]),
         "pcq_collector_points_device": (C.c_int, [vp, P(vp), P(u64)]),
@@ -254,7 +255,10 @@ def d3(v) -> "_D3":
 
 
 def buffer_address(buf) -> tuple[int, int]:
-    """(address, nbytes) of a bytes / bytearray / numpy / memoryview buffer without copying."""
+    """(address, nbytes) of a bytes / bytearray / numpy / memoryview buffer without copying; an (address, nbytes) pair
+    (memory the caller manages, e.g. a registered mapping) is passed through."""
+    if isinstance(buf, tuple):
+        return int(buf[0]), int(buf[1])
     if isinstance(buf, np.ndarray):
         assert buf.flags["C_CONTIGUOUS"]
         return buf.ctypes.data, buf.nbytes

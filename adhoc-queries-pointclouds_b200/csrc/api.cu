@@ -46,6 +46,21 @@ int use_device(pcq_ctx* ctx) {
 }
 
 // copy a small parameter table to the device through a ring of pinned slots (fully asynchronous)
+// two tables of one launch (its segments and its collectors) in ONE host-to-device copy: a small search is a handful of
+// microseconds of kernel behind a sequence of stream operations, each of which costs about as much
+int upload2(pcq_ctx* ctx, const void* a, size_t na, const void* b, size_t nb, void** dev_a, void** dev_b) {
+  const size_t off_b = round_up(na, 256);
+  std::vector<uint8_t>& tmp = ctx->upload_tmp;
+  tmp.resize(off_b + nb);
+  std::memcpy(tmp.data(), a, na);
+  std::memcpy(tmp.data() + off_b, b, nb);
+  void* d = nullptr;
+  RC(upload(ctx, tmp.data(), tmp.size(), &d));
+  *dev_a = d;
+  *dev_b = static_cast<uint8_t*>(d) + off_b;
+  return PCQ_OK;
+}
+
 int upload(pcq_ctx* ctx, const void* src, size_t bytes, void** dev_out) {
   UploadSlot& s = ctx->slots[ctx->next_slot];
   ctx->next_slot = (ctx->next_slot + 1) % kUploadSlots;
@@ -275,10 +290,38 @@ GridDev grid_view(const pcq_collector* c) {
 int grid_restore(pcq_collector* c) {
   if (!c->table_holds_winners) return PCQ_OK;
   GridDev g = grid_view(c);
-  if (launch_grid_final_phase(g, c->cand_len, 3, c->ctx->sm_count, c->ctx->stream) != 0)
-    return fail(PCQ_ERR_CUDA, "k_grid_final_phase launch failed");
+  if (launch_grid_final_restore(g, c->fin_max, c->d_finlist, &c->dev->fin_count, c->ctx->sm_count, c->ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_final_restore launch failed");
   c->ctx->launches++;
   c->table_holds_winners = false;
+  return PCQ_OK;
+}
+
+// finalisation, first half: list the finalists of the first n candidates and let the smallest scan index win each cell.
+// Afterwards the table holds winner codes (table_holds_winners) until grid_restore.
+int grid_pick_winners(pcq_collector* c, const GridDev& g, uint64_t n) {
+  pcq_ctx* ctx = c->ctx;
+  if (n >> 32) return fail(PCQ_ERR_NOMEM, "density finalisation: %llu candidates exceed the 32-bit finalist list", (unsigned long long)n);
+  if (c->finlist_cap < n) {
+    if (c->d_finlist) cudaFree(c->d_finlist);
+    c->d_finlist = nullptr;
+    c->finlist_cap = 0;
+    const uint64_t cap = n + n / 4 + 4096;
+    if (cudaMalloc(&c->d_finlist, cap * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PCQ_ERR_NOMEM, "cannot allocate the finalist list of %llu entries", (unsigned long long)cap);
+    }
+    c->finlist_cap = cap;
+  }
+  CU(cudaMemsetAsync(&c->dev->fin_count, 0, sizeof(unsigned long long), ctx->stream));
+  c->fin_max = n;
+  if (launch_grid_finalists(g, n, c->d_finlist, &c->dev->fin_count, ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_finalists launch failed");
+  c->table_holds_winners = true;  // from here on (also if a later launch fails); the distances go back lazily
+                                  // (grid_restore): usually nothing follows
+  if (launch_grid_final_min(g, n, c->d_finlist, &c->dev->fin_count, ctx->sm_count, ctx->stream) != 0)
+    return fail(PCQ_ERR_CUDA, "k_grid_final_min launch failed");
+  ctx->launches += 2;
   return PCQ_OK;
 }
 
@@ -486,14 +529,11 @@ int grid_finalize(pcq_collector* c) {
   if (n) {
     CU(cudaMemsetAsync(&c->dev->out_count, 0, sizeof(unsigned long long), ctx->stream));
     GridDev g = grid_view(c);
-    c->table_holds_winners = true;  // from the first phase on (also if a later launch fails); the distances go back
-                                    // lazily (grid_restore): usually nothing follows
-    for (int phase = 0; phase < 3; ++phase)
-      if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0)
-        return fail(PCQ_ERR_CUDA, "k_grid_final_phase launch failed");
-    if (launch_grid_emit(g, n, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count, ctx->sm_count, ctx->stream) != 0)
+    RC(grid_pick_winners(c, g, n));
+    if (launch_grid_emit(g, n, c->d_finlist, &c->dev->fin_count, 2, 1, nullptr, nullptr, nullptr, c->d_final, &c->dev->out_count,
+                         ctx->sm_count, ctx->stream) != 0)
       return fail(PCQ_ERR_CUDA, "k_grid_emit launch failed");
-    ctx->launches += 4;
+    ctx->launches += 1;
     DevBlock b;
     RC(read_devblock(c, &b));
     from_table = b.out_count;
@@ -564,8 +604,7 @@ int alias_slow_path(pcq_ctx* ctx, const std::vector<Segment>& segs, ScanParams P
       }
       void* d_segs = nullptr;
       void* d_lanes = nullptr;
-      RC(upload(ctx, segs.data(), segs.size() * sizeof(Segment), &d_segs));
-      RC(upload(ctx, lanes.data(), lanes.size() * sizeof(LaneDev), &d_lanes));
+      RC(upload2(ctx, segs.data(), segs.size() * sizeof(Segment), lanes.data(), lanes.size() * sizeof(LaneDev), &d_segs, &d_lanes));
       P.segs = static_cast<const Segment*>(d_segs);
       P.lanes = static_cast<const LaneDev*>(d_lanes);
       if (P.one_grid) P.grid0 = lanes[0].grid;
@@ -724,8 +763,7 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
     }
     void* d_segs = nullptr;
     void* d_lanes = nullptr;
-    RC(upload(ctx, segs.data(), segs.size() * sizeof(Segment), &d_segs));
-    RC(upload(ctx, lanes.data(), lanes.size() * sizeof(LaneDev), &d_lanes));
+    RC(upload2(ctx, segs.data(), segs.size() * sizeof(Segment), lanes.data(), lanes.size() * sizeof(LaneDev), &d_segs, &d_lanes));
 
     ScanParams P{};
     P.segs = static_cast<const Segment*>(d_segs);
@@ -1254,6 +1292,7 @@ void pcq_collector_destroy(pcq_collector* c) {
   if (c->grid.cands) cudaFree(c->grid.cands);
   if (c->d_final) cudaFree(c->d_final);
   if (c->d_export) cudaFree(c->d_export);
+  if (c->d_finlist) cudaFree(c->d_finlist);
   if (c->d_akeys) cudaFree(c->d_akeys);
   if (c->d_aord) cudaFree(c->d_aord);
   if (c->d_astates) cudaFree(c->d_astates);
@@ -1324,6 +1363,27 @@ int pcq_collector_reset(pcq_collector* c) {
   if (c->kind == PCQ_COLLECT_GRID) {
     CU(cudaMemsetAsync(c->grid.table, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
     if (c->grid.hkeys) CU(cudaMemsetAsync(c->grid.hkeys, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
+  }
+  return PCQ_OK;
+}
+
+int pcq_collectors_reset(pcq_collector* const* collectors, uint32_t n) {
+  if (!collectors && n) return fail(PCQ_ERR_ARG, "null collectors");
+  std::vector<pcq_collector*> rest;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!collectors[i]) return fail(PCQ_ERR_ARG, "null collector");
+    if (collectors[i]->kind == PCQ_COLLECT_GRID)
+      RC(pcq_collector_reset(collectors[i]));
+    else
+      rest.push_back(collectors[i]);
+  }
+  // per context, in one launch each
+  while (!rest.empty()) {
+    pcq_ctx* ctx = rest.front()->ctx;
+    std::vector<pcq_collector*> mine, other;
+    for (pcq_collector* c : rest) (c->ctx == ctx ? mine : other).push_back(c);
+    RC(reset_collectors_batched(ctx, mine.data(), mine.size()));
+    rest.swap(other);
   }
   return PCQ_OK;
 }
@@ -2152,12 +2212,11 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
   CU(cudaMemsetAsync(ctx->part_scratch, 0, 2ull * n_parts * sizeof(unsigned long long), ctx->stream));
   GridDev g = grid_view(c);
   g.own_parts = 0;                // every locally occupied cell is exported
-  c->table_holds_winners = true;  // until phase 3 below has put the distances back
-  for (int phase = 0; phase < 3; ++phase)
-    if (launch_grid_final_phase(g, n, phase, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");
-  if (launch_grid_emit(g, n, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
+  RC(grid_pick_winners(c, g, n));
+  if (launch_grid_emit(g, n, c->d_finlist, &c->dev->fin_count, 0, n_parts, ctx->part_scratch, nullptr, nullptr, nullptr, nullptr,
+                       ctx->sm_count, ctx->stream) != 0)
     return fail(PCQ_ERR_CUDA, "launch failed");
-  ctx->launches += 4;
+  ctx->launches += 1;
   std::vector<unsigned long long> h(n_parts);
   CU(cudaMemcpyAsync(h.data(), ctx->part_scratch, n_parts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -2178,12 +2237,11 @@ int pcq_grid_export_candidates(pcq_collector* c, uint32_t n_parts, const void** 
   }
   CU(cudaMemcpyAsync(ctx->part_scratch + n_parts, cursor.data(), n_parts * sizeof(unsigned long long),
                      cudaMemcpyHostToDevice, ctx->stream));
-  if (launch_grid_emit(g, n, 1, n_parts, ctx->part_scratch, ctx->part_scratch + n_parts, c->d_export, nullptr, nullptr,
-                       ctx->sm_count, ctx->stream) != 0)
+  if (launch_grid_emit(g, n, c->d_finlist, &c->dev->fin_count, 1, n_parts, ctx->part_scratch, ctx->part_scratch + n_parts, c->d_export,
+                       nullptr, nullptr, ctx->sm_count, ctx->stream) != 0)
     return fail(PCQ_ERR_CUDA, "launch failed");
-  if (launch_grid_final_phase(g, n, 3, ctx->sm_count, ctx->stream) != 0) return fail(PCQ_ERR_CUDA, "launch failed");  // distances back
-  c->table_holds_winners = false;
-  ctx->launches += 2;
+  ctx->launches += 1;
+  RC(grid_restore(c));  // distances back
   CU(cudaStreamSynchronize(ctx->stream));
   *out_dev_candidates = c->d_export;
   return PCQ_OK;

@@ -1025,9 +1025,6 @@ __global__ void __launch_bounds__(kBlock) k_scan_staged(ScanParams P) {
 // QUEUE = true (sparse matches, chosen by the host like MODE_GRIDQ): matching points are appended to a per-warp queue
 // in shared memory (no atomics: the warp is the only writer) and inserted 64 at a time with every lane busy.
 // ------------------------------------------------------------------------------------------------
-#ifndef PCQ_GRID_MINB
-#define PCQ_GRID_MINB 3
-#endif
 constexpr uint32_t kGsQFlush = 64;                // insert when a warp has queued this many matches
 template <int PPT>
 struct GsShape {
@@ -1097,11 +1094,13 @@ struct RegFetch {
   __device__ __forceinline__ unsigned long long gidx(const Segment&, int j) const { return gi0 + 32ull * (unsigned)j; }
 };
 
-// PPT: records per lane and tile.  The dense insert takes 4 (four consumer warps per CTA): a lane's four table reads
-// and its four chains of dependent FP64 operations are in flight together; the queue variant takes 2.
+// PPT: records per lane and tile (2: eight consumer warps per CTA).  Measured at navvis-XL: with 4 records per lane
+// (four consumer warps, 96 registers, four CTAs per SM) the insert takes 1.95 instead of 1.35 ms, and so does every
+// other way of putting more table reads in flight (56 registers and four CTAs: 1.80 ms; one ring per warp, 24 warps:
+// 1.82 ms) — the random reads of the cell table are bound by DRAM, not by the SMs' ability to issue them.
 // ONE: the launch has one collector — its grid is read from the kernel parameters (constant-bank operands).
 template <int R, int STAGES, bool QUEUE, int PPT, bool ONE>
-__global__ void __launch_bounds__(GsShape<PPT>::kThreads, QUEUE ? 2 : (PPT == 4 ? 4 : PCQ_GRID_MINB)) k_grid_scan(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(GsShape<PPT>::kThreads, QUEUE ? 2 : 3) k_grid_scan(const __grid_constant__ ScanParams P) {
   using Sh = GsShape<PPT>;
   constexpr int kWarps = Sh::kWarps;
   constexpr uint32_t kTileBytes = (uint32_t)kTilePts * (uint32_t)R;
@@ -2009,6 +2008,13 @@ constexpr int kSelBLag = 2;
 constexpr int kSelBDenseRecs = 128;
 constexpr int kSelBStageBytes = 4096;                                    // 128 * 31 + 15 phase bytes, rounded up
 constexpr int kSelBGatherBytes = kSelBDenseRecs * 12;                    // positions of one round
+constexpr int kSelBChunkRecs = 2 * kSelBGatherBytes / 32;                // sparse warp-units: records per round of 32-byte slots (96)
+#ifndef PCQ_SELB_CHUNKS
+#define PCQ_SELB_CHUNKS 1
+#endif
+#ifndef PCQ_SELB_CLASS_POLICY
+#define PCQ_SELB_CLASS_POLICY l2_policy_drop()
+#endif
 #ifndef PCQ_SELB_SEARCH_MAX
 #define PCQ_SELB_SEARCH_MAX 512
 #endif
@@ -2043,7 +2049,10 @@ __device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const 
   const Segment& S = U.seg;
   const uint64_t wbase = U.u0 + (uint64_t)w * warp_pts;
   const uint64_t pol = l2_policy_drop();
-  // lane l gathers, and later composes, matches l, l + 32, l + 64, l + 96 of a round: no other lane reads its slots
+  // lane l gathers, and later composes, matches l, l + 32, l + 64, l + 96 of a round: no other lane reads its slots.
+  // (Measured alternatives, both slower and with the same DRAM bytes: the words of a round gathered as one coalesced
+  // stream — lane t takes word t % 3 of match t / 3 — and, for sparse warp-units, the owner of a (row, lane) entry
+  // gathering its own matches without any search: profiles/r02_notes.md.)
   auto gather = [&](uint32_t base, uint32_t buf) {
     const uint32_t n = min((uint32_t)kSelBDenseRecs, mine - base);
     const uint32_t dst0 = smem_u32(gbuf + buf * (uint32_t)kSelBGatherBytes);
@@ -2095,6 +2104,73 @@ __device__ __forceinline__ void select_emit_warp_gather(const SelUnit& U, const 
   }
 }
 
+// k_select_bytes, SPARSE warp-units of colourless LAST files (a rare class: a few hundred matches among a warp's 4096
+// class bytes).  ncu on a 4 % class: 114 bytes of DRAM reads per gathered 12-byte position, and the kernel, moving
+// 2.2 GB for 0.9 GB of algorithmic bytes, runs at 5.6 TB/s of DRAM traffic — it is bound by what a random 12-byte read
+// costs in HBM, whatever the request looks like (three 4-byte requests, one coalesced word stream, aligned 16-byte
+// chunks, cudaLimitMaxL2FetchGranularity = 32: the same DRAM bytes every time, profiles/r02_notes.md).  What the request
+// shape does change is the work around it: a position fetched as the one or two aligned 16-byte chunks that hold it
+// (cp.async.cg: past L1, 1.5 requests per position instead of 3) makes the sparse select 4 % faster.  Each lane gathers
+// and later composes matches l, l + 32, l + 64 of a round of 96; a position's phase inside its first chunk stays in a
+// register.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <class IndexOf>
+__device__ __forceinline__ void select_emit_warp_chunks(const SelUnit& U, const IndexOf& index_of, uint32_t warp_pts, uint8_t* stage,
+                                                        uint8_t* gbuf /* kSelBChunkRecs * 32 bytes */, uint32_t cls) {
+  const uint32_t w = warp_id(), ln = lane_id();
+  const uint32_t mine = U.warp_cnt[w];
+  uint32_t before = 0;
+  for (uint32_t k = 0; k < w; ++k) before += U.warp_cnt[k];
+  const unsigned long long out0 = U.out_rec + before;
+  const Segment& S = U.seg;
+  const uint8_t* pos0 = S.rec + (U.u0 + (uint64_t)w * warp_pts) * 12ull;
+  const uint64_t pol = l2_policy_drop();
+  const uint32_t dst0 = smem_u32(gbuf);
+#pragma unroll 1
+  for (uint32_t base = 0; base < mine; base += (uint32_t)kSelBChunkRecs) {
+    const unsigned long long orec = out0 + base;
+    const unsigned long long g0 = orec * 31ull;
+    const uint32_t phase = (uint32_t)(g0 & 15ull);  // keep global and shared 16-byte phases equal
+    const uint32_t n = min((uint32_t)kSelBChunkRecs, mine - base);
+    uint32_t off[kSelBChunkRecs / 32];  // byte offset of the position inside its first chunk: 0, 4, 8 or 12
+#pragma unroll
+    for (uint32_t j = 0; j < (uint32_t)kSelBChunkRecs / 32u; ++j) {
+      const uint32_t r = ln + 32u * j;
+      off[j] = 0u;
+      if (r < n) {
+        const uint8_t* p = pos0 + index_of(base + r) * 12u;
+        off[j] = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+        const uint8_t* a = p - off[j];
+        cp_async16(dst0 + r * 32u, a);
+        if (off[j] > 4u) cp_async16(dst0 + r * 32u + 16u, a + 16);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+#pragma unroll
+    for (uint32_t j = 0; j < (uint32_t)kSelBChunkRecs / 32u; ++j) {
+      const uint32_t r = ln + 32u * j;
+      if (r < n) {
+        const int32_t* gp = reinterpret_cast<const int32_t*>(gbuf + r * 32u + off[j]);
+        RawPoint q;
+        q.x = gp[0];
+        q.y = gp[1];
+        q.z = gp[2];
+        q.cls = cls;
+        q.r = q.g = q.b = 0u;  // Vector3::new(0, 0, 0), last.rs:152
+        select_compose(S, q, stage + phase + r * 31u);
+      }
+    }
+    __syncwarp();
+    const unsigned long long room = orec < U.out_cap ? U.out_cap - orec : 0ull;
+    const uint32_t nb = (room < (unsigned long long)n ? (uint32_t)room : n) * 31u;
+    if (nb) select_flush<(kSelBChunkRecs * 31 + 15 + 511) / 512>(U.out, stage, g0, phase, nb, ln, pol);
+    __syncwarp();  // the staging and gather buffers are reused by the next round / unit
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MODE_SELECT for LAST class queries (last.rs:253-291): the predicate stream is ONE byte per point, so a 2048-point
 // unit would be 2 KB and the kernel would run at the unit rate of the look-back machinery, not at memory speed.
@@ -2129,14 +2205,18 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
 
   const uint32_t w = warp_id();
   const uint32_t pat = (P.cls & 0xFFu) * 0x01010101u;
-  const uint64_t pol_keep = l2_policy_keep();
+  // The class bytes are read once and never again (the emit works from the match masks): they stream through L2 with
+  // evict_first.  (They used to carry the `keep` policy of the record-reading select kernels, whose emit re-reads the
+  // matching records; here that pinned 1 byte per point of dead data in L2 and pushed out what IS re-read — the second
+  // and third word of every gathered position and the look-back descriptors.)
+  const uint64_t pol_stream = PCQ_SELB_CLASS_POLICY;
   uint4 v[kSelBRows];
   uint32_t npts = 0;  // points of the unit whose class bytes are in (or on their way into) v
   auto load_row = [&](const uint8_t* col, uint32_t n_unit, int k) {
     const uint32_t i = (uint32_t)k * 512u + ln * 16u;
     v[k] = make_uint4(0u, 0u, 0u, 0u);
     // a partly valid 16-byte group is still loadable: columns are followed by other columns or by padding
-    if (w * kSelBWarpPts + i < n_unit) v[k] = ldg_v4_h(col + i, pol_keep);
+    if (w * kSelBWarpPts + i < n_unit) v[k] = ldg_v4_h(col + i, pol_stream);
   };
   auto nibble = [&](uint32_t wd) -> uint32_t { return ((__vcmpeq4(wd, pat) & 0x08040201u) * 0x01010101u) >> 24; };
 
@@ -2244,7 +2324,9 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
             const uint32_t e = lo - 1u;  // holds the r-th match (an entry without matches never ends the search)
             return e * 16u + nth_set_bit((uint32_t)mk[e], r - (uint32_t)pr[e]);
           };
-          if (plain && mine > (uint32_t)kSelBDenseRecs)
+          if (plain && PCQ_SELB_CHUNKS)
+            select_emit_warp_chunks(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu);
+          else if (plain && mine > (uint32_t)kSelBDenseRecs)
             select_emit_warp_gather(EU, index_of, (uint32_t)kSelBWarpPts, stage_w, stage_w + kSelBStageBytes, P.cls & 0xFFu);
           else
             select_emit_warp<AL>(EU, index_of, (uint32_t)kSelBWarpPts, stage_w);
@@ -2339,7 +2421,32 @@ __global__ void __launch_bounds__(kBlock) k_class_count_soa(ScanParams P) {
 // ------------------------------------------------------------------------------------------------
 
 // keep only candidates that still hold their cell's minimum distance
-__global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count) {
+// Slot of this thread's item in an output that is appended to through ONE global counter: the block's items of this
+// iteration are counted in shared memory and placed with one atomic (a counter bumped once per warp serialises in its L2
+// atomic unit: 280 k same-address atomics were 0.3 of the 0.4 ms k_grid_finalists took at navvis-XL).  Block-convergent.
+__device__ __forceinline__ unsigned long long block_append(bool have, unsigned long long* counter, uint32_t* s_warp /* 8 */,
+                                                           unsigned long long* s_base) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, have);
+  const uint32_t w = warp_id(), ln = lane_id();
+  if (ln == 0) s_warp[w] = (uint32_t)__popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += s_warp[k];
+    *s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  unsigned long long at = *s_base;
+  for (uint32_t k = 0; k < w; ++k) at += s_warp[k];
+  at += (unsigned long long)__popc(bal & ((1u << ln) - 1u));
+  __syncthreads();  // s_warp / s_base are reused by the next iteration
+  return at;
+}
+
+__global__ void __launch_bounds__(256) k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_base;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n_in; i0 += stride) {
     const uint64_t i = i0 + threadIdx.x;
@@ -2361,14 +2468,9 @@ __global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned 
         c3 = c4[3];
       }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    if (bal == 0u) continue;
-    const uint32_t leader = (uint32_t)__ffs((int)bal) - 1u;
-    unsigned long long base = 0;
-    if (lane_id() == leader) base = atomicAdd(dst_count, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, (int)leader);
+    const unsigned long long at = block_append(keep, dst_count, s_warp, &s_base);
     if (keep) {
-      uint4* o4 = reinterpret_cast<uint4*>(dst + base + __popc(bal & ((1u << lane_id()) - 1u)));
+      uint4* o4 = reinterpret_cast<uint4*>(dst + at);
       o4[0] = c0;
       o4[1] = c1;
       o4[2] = c2;
@@ -2379,71 +2481,93 @@ __global__ void k_grid_prune(GridDev g, uint64_t n_in, Candidate* dst, unsigned 
 
 // Finalisation (HashMap::values, grid_sampling.rs:111-113) works IN PLACE: the distance table doubles as the
 // per-cell "smallest scan index among the candidates at the minimum distance" table, so a 2^27-cell grid needs no
-// second 1 GB array (and no 1 GB memset per finalisation).  One launch per phase, all over the candidate arena:
-//   phase 0  flag the candidates that sit at their cell's minimum distance ("finalists"; byte 55 of the candidate)
-//   phase 1  finalists clear their cell:                table[slot] = ~0
-//   phase 2  the smallest scan index wins:              atomicMin(table[slot], scan index)
-//   emit     k_grid_emit (winner == finalist whose scan index is in the table)
-//   phase 3  finalists put the distance back:           table[slot] = dist bits   (the collector can go on collecting)
-__global__ void k_grid_final_phase(GridDev g, uint64_t n, int phase) {
+// second 1 GB array (and no 1 GB memset per finalisation).  All over the candidate arena's FINALISTS:
+//   k_grid_finalists      list the candidates that sit at their cell's minimum distance (about a quarter of the arena
+//                         in dense data; every later step reads only those)
+//   k_grid_final_min      the smallest scan index wins:  atomicMax(table[slot], winner code)
+//   k_grid_emit           winner == finalist whose code is in the table
+//   k_grid_final_restore  finalists put the distance back: table[slot] = dist bits   (the collector can go on collecting)
+// A winner code has bit 63 set — no distance has (they are non-negative doubles) — and grows as the scan index
+// shrinks, so ONE atomicMax both replaces the distance and keeps the first point in scan order (strict `<` of :97-102).
+// (Round 1 kept a finalist flag in the candidates and walked the whole arena four times, two 32-byte sectors per
+// candidate and pass: 0.96 ms at navvis-XL, as long as the insert itself.)
+constexpr unsigned long long kWinTag = 1ull << 63, kWinClaim = 1ull << 62, kWinIdxMask = (1ull << 62) - 1ull;
+__device__ __forceinline__ unsigned long long win_code(unsigned long long scan_idx) {
+  return kWinTag | (kWinIdxMask - (scan_idx & kWinIdxMask));
+}
+
+__global__ void __launch_bounds__(256) k_grid_finalists(GridDev g, uint64_t n, uint32_t* list, unsigned long long* list_count) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_base;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    Candidate& c = g.cands[i];
-    if (c.scan_idx == kCandEmpty) continue;
-    if (phase == 0) {
-      bool fin = false;
-      const bool mine = g.own_parts <= 1u || (uint32_t)(mix64(c.key) % g.own_parts) == g.own_me;  // multi-GPU: owner only
-      if (mine && alias_find(g, c.key) == ~0u) {  // affected keys come from the replay
-        const uint64_t slot = grid_slot(g, c.key, false);
-        fin = slot != ~0ull && g.table[slot] == c.dist_bits;
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+    const uint64_t i = i0 + threadIdx.x;
+    bool fin = false;
+    if (i < n) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(g.cands + i);
+      const uint4 c0 = c4[0];
+      const uint2 c1 = *reinterpret_cast<const uint2*>(c4 + 1);  // scan index (same 32-byte sector)
+      const uint64_t key = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
+      const unsigned long long d = (unsigned long long)c0.z | ((unsigned long long)c0.w << 32);
+      const unsigned long long sidx = (unsigned long long)c1.x | ((unsigned long long)c1.y << 32);
+      const bool mine = g.own_parts <= 1u || (uint32_t)(mix64(key) % g.own_parts) == g.own_me;  // multi-GPU: owner only
+      if (sidx != kCandEmpty && mine && alias_find(g, key) == ~0u) {  // affected keys come from the replay
+        const uint64_t slot = grid_slot(g, key, false);
+        fin = slot != ~0ull && g.table[slot] == d;
       }
-      c.pad_[0] = fin ? 1 : 0;
-      continue;
     }
-    if (!c.pad_[0]) continue;
-    const uint64_t slot = grid_slot(g, c.key, false);
-    if (phase == 1)
-      g.table[slot] = ~0ull;
-    else if (phase == 2)
-      atomicMin(g.table + slot, (unsigned long long)c.scan_idx);
-    else
-      g.table[slot] = c.dist_bits;
+    const unsigned long long at = block_append(fin, list_count, s_warp, &s_base);
+    if (fin) list[at] = (uint32_t)i;
+  }
+}
+
+__global__ void k_grid_final_min(GridDev g, const uint32_t* list, const unsigned long long* list_count) {
+  const uint64_t m = *list_count, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const Candidate& c = g.cands[list[j]];
+    atomicMax(g.table + grid_slot(g, c.key, false), win_code((unsigned long long)c.scan_idx));
+  }
+}
+
+__global__ void k_grid_final_restore(GridDev g, const uint32_t* list, const unsigned long long* list_count) {
+  const uint64_t m = *list_count, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const Candidate& c = g.cands[list[j]];
+    g.table[grid_slot(g, c.key, false)] = c.dist_bits;
   }
 }
 
 // winners -> 31-byte records (order arbitrary, like HashMap::values) or -> per-owner candidate parts
 // mode 0: count per part, mode 1: write candidates into parts, mode 2: write 31-byte points
-// (between phase 2 and phase 3 of the finalisation: table[slot] holds the winning scan index)
-__global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
-                            unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points,
-                            unsigned long long* out_count) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+// (between k_grid_final_min and k_grid_final_restore: table[slot] holds the winner's code)
+__global__ void __launch_bounds__(256) k_grid_emit(GridDev g, const uint32_t* list, const unsigned long long* list_count, int mode, uint32_t n_parts,
+                            unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
+                            uint8_t* out_points, unsigned long long* out_count) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_base;
+  const uint64_t m = *list_count, stride = (uint64_t)gridDim.x * blockDim.x;
   if (mode == 2) {
-    // winners -> 31-byte points.  One atomic per warp (not per winner) on the single output counter; a record goes out
-    // as the same 14 stores sts_point31 uses, so the winners of a warp fill one contiguous stretch of the output.
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
-      const uint64_t i = i0 + threadIdx.x;
+    // winners -> 31-byte points.  One atomic per block and iteration on the single output counter; a record goes out
+    // as the same 14 stores sts_point31 uses, so the winners of a block fill one contiguous stretch of the output.
+    for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x; j0 < m; j0 += stride) {
+      const uint64_t j = j0 + threadIdx.x;
       bool win = false;
-      if (i < n) {
+      uint64_t i = 0;
+      if (j < m) {
+        i = list[j];
         const Candidate& c = g.cands[i];
-        if (c.scan_idx != kCandEmpty && c.pad_[0]) {
-          unsigned long long* cell = g.table + grid_slot(g, c.key, false);
-          const unsigned long long mine = (unsigned long long)c.scan_idx;
-          win = *cell == mine && atomicCAS(cell, mine, mine | (1ull << 63)) == mine;
-        }
+        unsigned long long* cell = g.table + grid_slot(g, c.key, false);
+        const unsigned long long mine = win_code((unsigned long long)c.scan_idx);
+        // (claimed once even if the arena holds the same point twice)
+        win = *cell == mine && atomicCAS(cell, mine, mine | kWinClaim) == mine;
       }
-      const uint32_t bal = __ballot_sync(0xffffffffu, win);
-      if (bal == 0u) continue;
-      const uint32_t leader = (uint32_t)__ffs((int)bal) - 1u;
-      unsigned long long base = 0;
-      if (lane_id() == leader) base = atomicAdd(out_count, (unsigned long long)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, (int)leader);
+      const unsigned long long at = block_append(win, out_count, s_warp, &s_base);
       if (win) {
         const uint4* s4 = reinterpret_cast<const uint4*>(g.cands + i);  // the point sits at byte 24 of the candidate
         const uint4 a = s4[1], b = s4[2], c3 = s4[3];
         // bytes 24..54 of the candidate: a.z a.w | b.x b.y b.z b.w | c3.x c3.y (low 3 bytes)
         const uint32_t w[8] = {a.z, a.w, b.x, b.y, b.z, b.w, c3.x, c3.y & 0x00FFFFFFu};
-        stg_point31(out_points + (base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u))) * 31ull, w);
+        stg_point31(out_points + at * 31ull, w);
       }
     }
     return;
@@ -2451,27 +2575,25 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, u
   // Modes 0 and 1 (owner partitioning of the multi-GPU exchange).  The per-part counters are a handful of addresses:
   // one atomic per winner serialised 2.4 M atomics on 2-8 words (2.9 ms of export at navvis-XL on two GPUs), so the
   // winners of a warp that go to the same part are counted / placed with ONE atomic (__match_any_sync on the part).
-  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
-    const uint64_t i = i0 + threadIdx.x;
+  for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x; j0 < m; j0 += stride) {
+    const uint64_t j = j0 + threadIdx.x;
     bool win = false;
     uint32_t part = 0xFFFFFFFFu;
-    unsigned long long* cell = nullptr;
-    unsigned long long mine = 0;
-    if (i < n) {
+    uint64_t i = 0;
+    if (j < m) {
+      i = list[j];
       const Candidate& c = g.cands[i];
-      if (c.scan_idx != kCandEmpty && c.pad_[0]) {
-        cell = g.table + grid_slot(g, c.key, false);
-        mine = (unsigned long long)c.scan_idx;
-        const unsigned long long claimed = mine | (1ull << 63);
-        if (mode == 0) {
-          // count the winner once even if the candidate list holds duplicates of it
-          win = *cell == mine && atomicCAS(cell, mine, claimed) == mine;
-        } else {
-          // second walk after mode 0: claimed entries carry bit 63; release the claim while emitting
-          win = *cell == claimed && atomicCAS(cell, claimed, mine) == claimed;
-        }
-        if (win) part = (uint32_t)(mix64(c.key) % n_parts);
+      unsigned long long* cell = g.table + grid_slot(g, c.key, false);
+      const unsigned long long mine = win_code((unsigned long long)c.scan_idx);
+      const unsigned long long claimed = mine | kWinClaim;
+      if (mode == 0) {
+        // count the winner once even if the candidate list holds duplicates of it
+        win = *cell == mine && atomicCAS(cell, mine, claimed) == mine;
+      } else {
+        // second walk after mode 0: claimed entries carry the claim bit; release the claim while emitting
+        win = *cell == claimed && atomicCAS(cell, claimed, mine) == claimed;
       }
+      if (win) part = (uint32_t)(mix64(c.key) % n_parts);
     }
     const uint32_t peers = __match_any_sync(0xffffffffu, part);  // lanes of this warp that go to the same part
     if (!win) continue;
@@ -2494,7 +2616,9 @@ __global__ void k_grid_emit(GridDev g, uint64_t n, int mode, uint32_t n_parts, u
 }
 
 // fold candidates received from peers into the table (multi-GPU density merge)
-__global__ void k_grid_import(GridDev g, const Candidate* in, uint64_t n) {
+__global__ void __launch_bounds__(256) k_grid_import(GridDev g, const Candidate* in, uint64_t n) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_base;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
     const uint64_t i = i0 + threadIdx.x;
@@ -2516,14 +2640,8 @@ __global__ void k_grid_import(GridDev g, const Candidate* in, uint64_t n) {
         want = d <= old;
       }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, want);
-    if (bal == 0u) continue;
-    const uint32_t leader = (uint32_t)__ffs((int)bal) - 1u;
-    unsigned long long base = 0;
-    if (lane_id() == leader) base = atomicAdd(g.cand_count, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, (int)leader);
+    const unsigned long long ci = block_append(want, g.cand_count, s_warp, &s_base);
     if (want) {
-      const unsigned long long ci = base + (unsigned long long)__popc(bal & ((1u << lane_id()) - 1u));
       if (ci < g.cand_cap) {
         uint4* o4 = reinterpret_cast<uint4*>(g.cands + ci);
         o4[0] = c0;
@@ -2614,15 +2732,9 @@ static int launch_grid_scan_r(const ScanParams& p, uint32_t R, int sm_count, cud
   }
 }
 static int launch_grid_scan(const ScanParams& p, uint32_t R, int sm_count, cudaStream_t st) {
-  static const int dense_ppt = [] {
-    const char* e = std::getenv("PCQ_GRID_PPT");  // measurement only
-    return e ? std::atoi(e) : 2;
-  }();
   if (p.grid_sparse)
     return p.one_grid ? launch_grid_scan_r<true, 2, true>(p, R, sm_count, st) : launch_grid_scan_r<true, 2, false>(p, R, sm_count, st);
-  if (dense_ppt == 2)
-    return p.one_grid ? launch_grid_scan_r<false, 2, true>(p, R, sm_count, st) : launch_grid_scan_r<false, 2, false>(p, R, sm_count, st);
-  return p.one_grid ? launch_grid_scan_r<false, 4, true>(p, R, sm_count, st) : launch_grid_scan_r<false, 4, false>(p, R, sm_count, st);
+  return p.one_grid ? launch_grid_scan_r<false, 2, true>(p, R, sm_count, st) : launch_grid_scan_r<false, 2, false>(p, R, sm_count, st);
 }
 
 template <int MODE>
@@ -2771,18 +2883,31 @@ int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned 
   return check_launch();
 }
 
-int launch_grid_final_phase(const GridDev& g, uint64_t n, int phase, int sm_count, void* stream) {
+int launch_grid_finalists(const GridDev& g, uint64_t n, uint32_t* list, unsigned long long* list_count, int sm_count, void* stream) {
   if (n == 0) return 0;
-  k_grid_final_phase<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, phase);
+  k_grid_finalists<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, list, list_count);
+  return check_launch();
+}
+// (the list's length lives on the device; n_max, the number of candidates it was made from, sizes the grid)
+int launch_grid_final_min(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int sm_count,
+                          void* stream) {
+  if (n_max == 0) return 0;
+  k_grid_final_min<<<grid_for(n_max, sm_count), 256, 0, (cudaStream_t)stream>>>(g, list, list_count);
+  return check_launch();
+}
+int launch_grid_final_restore(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int sm_count,
+                              void* stream) {
+  if (n_max == 0) return 0;
+  k_grid_final_restore<<<grid_for(n_max, sm_count), 256, 0, (cudaStream_t)stream>>>(g, list, list_count);
   return check_launch();
 }
 
-int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
-                     unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points, unsigned long long* out_count,
-                     int sm_count, void* stream) {
-  if (n == 0) return 0;
-  k_grid_emit<<<grid_for(n, sm_count), 256, 0, (cudaStream_t)stream>>>(g, n, mode, n_parts, part_counts, part_cursor, out_cands,
-                                                                         out_points, out_count);
+int launch_grid_emit(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int mode,
+                     uint32_t n_parts, unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
+                     uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream) {
+  if (n_max == 0) return 0;
+  k_grid_emit<<<grid_for(n_max, sm_count), 256, 0, (cudaStream_t)stream>>>(g, list, list_count, mode, n_parts, part_counts, part_cursor,
+                                                                             out_cands, out_points, out_count);
   return check_launch();
 }
 

@@ -151,13 +151,18 @@ int launch_scan(int variant, int mode, const ScanParams& p, uint32_t uniform_rec
 int launch_class_count_soa(const ScanParams& p, int sm_count, void* stream);
 int launch_grid_prune(const GridDev& g, uint64_t n_in, Candidate* dst, unsigned long long* dst_count, int sm_count,
                       void* stream);
-// in-place finalisation of a density table (kernels.cu): phase 0 flag finalists, 1 clear their cells, 2 smallest scan
-// index wins, [launch_grid_emit], 3 put the distances back
-int launch_grid_final_phase(const GridDev& g, uint64_t n, int phase, int sm_count, void* stream);
-// mode 0: count winners per owner part, 1: write winners as candidates into their parts, 2: write 31-byte points
-int launch_grid_emit(const GridDev& g, uint64_t n, int mode, uint32_t n_parts, unsigned long long* part_counts,
-                     unsigned long long* part_cursor, Candidate* out_cands, uint8_t* out_points, unsigned long long* out_count,
-                     int sm_count, void* stream);
+// in-place finalisation of a density table (kernels.cu): [finalists] list the candidates that sit at their cell's
+// minimum distance, [final_min] the smallest scan index among them wins the cell (the table then holds winner codes
+// instead of distances), [emit], [final_restore] the finalists put the distances back
+int launch_grid_finalists(const GridDev& g, uint64_t n, uint32_t* list, unsigned long long* list_count, int sm_count, void* stream);
+int launch_grid_final_min(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int sm_count,
+                          void* stream);
+int launch_grid_final_restore(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int sm_count,
+                              void* stream);
+// over the finalists; mode 0: count winners per owner part, 1: write winners as candidates into their parts, 2: write 31-byte points
+int launch_grid_emit(const GridDev& g, uint64_t n_max, const uint32_t* list, const unsigned long long* list_count, int mode,
+                     uint32_t n_parts, unsigned long long* part_counts, unsigned long long* part_cursor, Candidate* out_cands,
+                     uint8_t* out_points, unsigned long long* out_count, int sm_count, void* stream);
 int launch_gather_blocks(const LaneDev* lanes, uint32_t n, uint32_t block_bytes, void* out, void* stream);
 int launch_grid_import(const GridDev& g, const Candidate* in, uint64_t n, int sm_count, void* stream);
 

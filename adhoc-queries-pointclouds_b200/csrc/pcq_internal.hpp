@@ -30,6 +30,7 @@ struct DevBlock {
   uint32_t flags;
   uint32_t pad_;
   unsigned long long log_count;   // GRID: replay-log entries written by the last launch (affected keys, alias.cu)
+  unsigned long long fin_count;   // GRID finalisation: entries of the finalist list
 };
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -56,6 +57,7 @@ struct pcq_ctx {
   uint64_t launches = 0;
   UploadSlot slots[kUploadSlots];
   int next_slot = 0;
+  std::vector<uint8_t> upload_tmp;  // staging of upload2
   // MODE_SELECT scratch
   unsigned long long* tile_state = nullptr;  // [0] = ticket, [1..] = descriptors
   uint64_t tile_state_cap = 0;
@@ -161,6 +163,10 @@ struct pcq_collector {
   // export scratch
   Candidate* d_export = nullptr;
   uint64_t export_cap = 0;
+  // finalisation: indices of the candidates that sit at their cell's minimum distance (count: dev->fin_count)
+  uint32_t* d_finlist = nullptr;
+  uint64_t finlist_cap = 0;
+  uint64_t fin_max = 0;  // candidates the list was made from (upper bound of its length, sizes the launches)
   // host copy of points()
   void* h_pts = nullptr;
   uint64_t h_cap = 0;
@@ -178,6 +184,7 @@ struct HostRange {
 
 int use_device(pcq_ctx* ctx);
 int upload(pcq_ctx* ctx, const void* src, size_t bytes, void** dev_out);
+int upload2(pcq_ctx* ctx, const void* a, size_t na, const void* b, size_t nb, void** dev_a, void** dev_b);
 GridDev grid_view(const pcq_collector* c);
 int grid_restore(pcq_collector* c);
 int grow_log(pcq_collector* c, uint64_t need);

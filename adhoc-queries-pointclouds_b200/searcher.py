@@ -209,6 +209,13 @@ class ResultCollector:
             pass
 
 
+def reset_collectors(collectors: Sequence[ResultCollector]) -> None:
+    """pcq_collectors_reset: clear a list of collectors (one kernel launch per context for count / buffer collectors)."""
+    n = len(collectors)
+    if n:
+        check(lib.pcq_collectors_reset((C.c_void_p * n)(*[c.handle for c in collectors]), n))
+
+
 class CountCollector(ResultCollector):
     kind = B.COLLECT_COUNT
 

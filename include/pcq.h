@@ -175,6 +175,10 @@ int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const dou
 void pcq_collector_destroy(pcq_collector* c);
 /* Forget everything collected so far (keeps allocations). */
 int pcq_collector_reset(pcq_collector* c);
+/* pcq_collector_reset for a list of collectors (e.g. the per-file collectors of run_search_parallel before the next
+ * query): the count and buffer collectors of a context are cleared by ONE kernel launch instead of one stream operation
+ * each; grid collectors are reset one by one. */
+int pcq_collectors_reset(pcq_collector* const* collectors, uint32_t n);
 /* ResultCollector::point_count (collect_points.rs:11). */
 int pcq_collector_point_count(pcq_collector* c, uint64_t* out);
 /* ResultCollector::points / points_ref (collect_points.rs:9-10): host array owned by the collector,

@@ -719,3 +719,27 @@ def test_las_records_on_device_equal_the_restated_file_dumper(pcq, ctx, n):
         assert np.array_equal(rec[:, 15], e["cls"]) and (rec[:, 14] == 0x09).all()
         assert np.array_equal(np.ascontiguousarray(rec[:, 20:26]).view("<u2").reshape(-1, 3), e["rgb"])
         assert not rec[:, [12, 13, 16, 17, 18, 19]].any()
+
+
+def test_batched_collector_reset(pcq, ctx):
+    """pcq_collectors_reset clears count, buffer and grid collectors like pcq_collector_reset does one by one."""
+    rng = np.random.default_rng(41)
+    files = [make_file(rng.integers(0, 100_000, size=(5000 + 100 * k, 3)), rng.integers(1, 4, size=5000 + 100 * k), fmt=1, seed=k)
+             for k in range(5)]
+    exts = ["las"] * len(files)
+    box1, box2 = ((0.0, 0.0, 0.0), (600.0, 900.0, 1000.0)), ((100.0, 0.0, 0.0), (1000.0, 300.0, 500.0))
+    grid = ((0.0, 0.0, 0.0), (1000.0, 1000.0, 1000.0), 50.0)
+    images = list(zip(files, exts))
+    for kind in (orc.COLLECT_COUNT, orc.COLLECT_BUFFER, orc.COLLECT_GRID):
+        def new():
+            if kind == orc.COLLECT_GRID:
+                return pcq.GridSampledCollector(*grid, ctx=ctx)
+            return (pcq.CountCollector if kind == orc.COLLECT_COUNT else pcq.BufferCollector)(ctx)
+
+        cols = [new() for _ in files]
+        pcq.BoundsSearcher(*box1).search_files(images, _impl(pcq), cols)
+        assert_same(kind, cols, oracle_run(files, exts, kind, bounds=box1, grid=grid, per_file=True))
+        pcq.reset_collectors(cols)
+        assert [c.point_count() for c in cols] == [0] * len(cols)
+        pcq.BoundsSearcher(*box2).search_files(images, _impl(pcq), cols)
+        assert_same(kind, cols, oracle_run(files, exts, kind, bounds=box2, grid=grid, per_file=True))
