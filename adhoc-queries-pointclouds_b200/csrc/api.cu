@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cctype>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -458,10 +459,103 @@ int alloc_grid_tables(pcq_collector* c, uint64_t slots, bool hashed) {
   return PCQ_OK;
 }
 
-// hashed table full: quadruple it and re-insert the surviving candidates
+// Cell tables of the grid collectors of one call that do not have one yet.  `boxes` (6 doubles per collector: min xyz,
+// max xyz; may be null) bounds the positions the collector can be fed in this call — the header boxes of its files,
+// cut by the query box.  In order of preference:
+//   dense over the sub-box of cells under `boxes` — when that is at most half of the grid and fits the budget;
+//   dense over the whole grid (slot == key) — when the key has at most 30 bits and it fits the budget;
+//   an open-addressing hash that starts small and is quadrupled on demand.
+// The budget is a third of the free HBM shared by the collectors of the call that need a table: `query --parallel
+// --density` makes one grid per file, and 64 dense ca13-XL tables would be 512 GB.  Results do not depend on the choice.
+static bool cell_range(const GridDev& g, int a, double lo, double hi, uint64_t* c_lo, uint64_t* c_n) {
+  if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi) || !(g.ext[a] > 0.0) || !std::isfinite(g.ext[a])) return false;
+  auto cell = [&](double p) -> double {
+    const double r = ((p - g.bmin[a]) * g.dims_f[a]) / g.ext[a];  // :51-57 (any rounding difference is inside the margin)
+    return r > 0.0 ? std::floor(r) : 0.0;
+  };
+  // (positions outside the grid's own box still have cells — 0 below it, up to the mask above it, beyond the mask they
+  // are aliased and bypass the table: the range is NOT cut to the grid box)
+  const double cmax = (double)g.mask[a];
+  double l = cell(lo) - 1.0, h = cell(hi) + 1.0;
+  l = std::min(std::max(l, 0.0), cmax);
+  h = std::min(std::max(h, l), cmax);
+  *c_lo = (uint64_t)l;
+  *c_n = (uint64_t)(h - l) + 1ull;
+  return true;
+}
+
+int ensure_grid_tables(pcq_collector* const* cols, uint32_t n, const double* boxes) {
+  // an EMPTY collector (fresh, or reset) whose sub-box table does not cover the box of this call gets a new table
+  for (uint32_t i = 0; i < n && boxes; ++i) {
+    pcq_collector* c = cols[i];
+    GridDev& g = c->grid;
+    if (c->kind != PCQ_COLLECT_GRID || !g.table || g.hkeys || !g.sub_on || c->cand_len != 0 || !c->akeys.empty()) continue;
+    const double* bx = boxes + 6 * (size_t)i;
+    bool inside = true;
+    for (int a = 0; a < 3 && inside; ++a) {
+      uint64_t lo = 0, nn = 0;
+      inside = cell_range(g, a, bx[a], bx[3 + a], &lo, &nn) && lo >= g.sub_lo[a] && lo + nn <= g.sub_lo[a] + g.sub_n[a];
+    }
+    if (inside) continue;
+    CU(cudaStreamSynchronize(c->ctx->stream));
+    cudaFree(g.table);
+    g.table = nullptr;
+    g.sub_on = 0;
+    c->table_holds_winners = false;
+  }
+  uint32_t missing = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (cols[i]->kind == PCQ_COLLECT_GRID && !cols[i]->grid.table) ++missing;
+  if (!missing) return PCQ_OK;
+  uint64_t dense_bits = 30;
+  if (const char* e = std::getenv("PCQ_DENSE_MAX_BITS")) dense_bits = (uint64_t)std::atoi(e);
+  bool use_sub = true;
+  if (const char* e = std::getenv("PCQ_GRID_SUBBOX")) use_sub = std::atoi(e) != 0;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const uint64_t budget = (uint64_t)free_b / 3 / missing;
+  for (uint32_t i = 0; i < n; ++i) {
+    pcq_collector* c = cols[i];
+    if (c->kind != PCQ_COLLECT_GRID || c->grid.table) continue;
+    GridDev& g = c->grid;
+    const bool dense_full = c->total_bits <= dense_bits && (8ull << c->total_bits) <= budget;
+    g.sub_on = 0;
+    if (use_sub && boxes) {
+      const double* bx = boxes + 6 * (size_t)i;
+      uint64_t lo[3], nn[3];
+      bool ok = true;
+      for (int a = 0; a < 3 && ok; ++a) ok = cell_range(g, a, bx[a], bx[3 + a], &lo[a], &nn[a]);
+      if (ok) {
+        const long double cells = (long double)nn[0] * (long double)nn[1] * (long double)nn[2];
+        const long double full = std::ldexp(1.0L, (int)c->total_bits);
+        if (cells * 8.0L <= (long double)budget && (!dense_full || cells * 2.0L <= full)) {
+          for (int a = 0; a < 3; ++a) {
+            g.sub_lo[a] = lo[a];
+            g.sub_n[a] = nn[a];
+          }
+          g.sub_on = 1;
+          RC(alloc_grid_tables(c, nn[0] * nn[1] * nn[2], false));
+          continue;
+        }
+      }
+    }
+    uint64_t slots = dense_full ? (1ull << c->total_bits) : (1ull << 22);
+    if (const char* e = std::getenv("PCQ_HASH_SLOTS_LOG2"))
+      if (!dense_full) slots = 1ull << std::atoi(e);
+    RC(alloc_grid_tables(c, slots, !dense_full));
+  }
+  return PCQ_OK;
+}
+
+// hashed table full: quadruple it and re-insert the surviving candidates (a sub-box table that met a cell outside its
+// box: replace it by a table over the whole grid)
 int rehash_grid(pcq_collector* c) {
   pcq_ctx* ctx = c->ctx;
-  RC(prune_cands(c));
+  const bool was_sub = c->grid.table && c->grid.hkeys == nullptr && c->grid.sub_on;
+  // (a sub-box table only moves: every candidate of the earlier launches is folded into the new table, nothing is
+  // pruned, so an ordered replay of aliased keys met in the same launch still finds what it needs)
+  if (was_sub) RC(grid_restore(c));
+  else RC(prune_cands(c));
   const uint64_t kept = c->cand_len;
   Candidate* tmp = nullptr;
   if (kept) {
@@ -469,10 +563,19 @@ int rehash_grid(pcq_collector* c) {
     CU(cudaMemcpyAsync(tmp, c->grid.cands, kept * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  const uint64_t old_slots = c->grid.table_slots;
   cudaFree(c->grid.table);
   cudaFree(c->grid.hkeys);
   c->grid.table = c->grid.hkeys = nullptr;
-  int rc = alloc_grid_tables(c, c->grid.table_slots * 4ull, true);
+  int rc;
+  if (was_sub) {
+    // a cell outside the sub-box the table was made for: from now on a table over the whole grid
+    c->grid.sub_on = 0;
+    pcq_collector* one = c;
+    rc = ensure_grid_tables(&one, 1, nullptr);
+  } else {
+    rc = alloc_grid_tables(c, old_slots * 4ull, true);
+  }
   if (rc != PCQ_OK) {
     cudaFree(tmp);
     return rc;
@@ -658,8 +761,37 @@ double expected_match_fraction(const pcq_file_desc& d, const pcq_query* q) {
 // of chunk runs an indexed launch can hold (those take the tile-scheduled scan)
 constexpr size_t kSoaCountMaxSegs = 256;
 
+// Where the positions a collector is fed in one call can lie: the union of the header boxes of its files, cut by the
+// query box of a bounds query (6 doubles per collector: min xyz, max xyz; a collector without a file keeps an empty box).
+struct LaneBoxes {
+  std::vector<double> v;
+  explicit LaneBoxes(uint32_t n) : v(6 * (size_t)n) {
+    for (uint32_t l = 0; l < n; ++l)
+      for (int a = 0; a < 3; ++a) {
+        v[6 * (size_t)l + a] = INFINITY;
+        v[6 * (size_t)l + 3 + a] = -INFINITY;
+      }
+  }
+  void add(uint32_t lane, const pcq_file_desc& d) {
+    for (int a = 0; a < 3; ++a) {
+      v[6 * (size_t)lane + a] = std::min(v[6 * (size_t)lane + a], d.hdr_min[a]);
+      v[6 * (size_t)lane + 3 + a] = std::max(v[6 * (size_t)lane + 3 + a], d.hdr_max[a]);
+    }
+  }
+  void cut(const pcq_query* q) {
+    if (q->kind != PCQ_QUERY_BOUNDS) return;
+    for (size_t l = 0; l < v.size() / 6; ++l)
+      for (int a = 0; a < 3; ++a) {
+        v[6 * l + a] = std::max(v[6 * l + a], q->qmin[a]);
+        v[6 * l + 3 + a] = std::min(v[6 * l + 3 + a], q->qmax[a]);
+      }
+  }
+};
+
+// lane_box (optional, 6 doubles per collector): where the positions fed to the collector in this call can lie
 int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_collector* const* collectors,
-              uint32_t n_collectors, const std::vector<uint64_t>& lane_points, double match_fraction = -1.0) {
+              uint32_t n_collectors, const std::vector<uint64_t>& lane_points, double match_fraction = -1.0,
+              const std::vector<double>* lane_box = nullptr) {
   const int kind = collectors[0]->kind;
   if (segs.empty()) return PCQ_OK;
 
@@ -723,6 +855,16 @@ int run_batch(pcq_ctx* ctx, std::vector<Segment>& segs, const pcq_query* q, pcq_
       RC(grow_out(c, c->out_len + guess));
     }
   } else if (kind == PCQ_COLLECT_GRID) {
+    {  // (collectors whose files the query does not touch need no table)
+      std::vector<pcq_collector*> active;
+      std::vector<double> boxes;
+      for (uint32_t l = 0; l < n_collectors; ++l) {
+        if (lane_points[l] == 0) continue;
+        active.push_back(collectors[l]);
+        if (lane_box) boxes.insert(boxes.end(), lane_box->begin() + 6 * (size_t)l, lane_box->begin() + 6 * (size_t)l + 6);
+      }
+      RC(ensure_grid_tables(active.data(), (uint32_t)active.size(), lane_box ? boxes.data() : nullptr));
+    }
     for (uint32_t l = 0; l < n_collectors; ++l) {
       pcq_collector* c = collectors[l];
       if (lane_points[l] == 0) continue;
@@ -1263,19 +1405,9 @@ int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const dou
       pcq_collector_destroy(c);
       return fail(PCQ_ERR_GRID, "SparseGrid key shifts of 64 bits are not representable");
     }
-    uint64_t dense_bits = 30;
-    if (const char* e = std::getenv("PCQ_DENSE_MAX_BITS")) dense_bits = (uint64_t)std::atoi(e);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    bool dense = total_bits <= dense_bits && (8ull << total_bits) <= free_b / 3;
-    uint64_t slots = dense ? (1ull << total_bits) : (1ull << 22);
-    if (const char* e = std::getenv("PCQ_HASH_SLOTS_LOG2"))
-      if (!dense) slots = 1ull << std::atoi(e);
-    rc = alloc_grid_tables(c, slots, !dense);
-    if (rc != PCQ_OK) {
-      pcq_collector_destroy(c);
-      return rc;
-    }
+    // the cell table is allocated when the collector is first used (ensure_grid_tables): only then is it known how
+    // many grids share the HBM — `query --parallel --density` makes one per file, and 64 dense ca13-XL tables are 512 GB
+    c->total_bits = total_bits;
   }
   *out = c;
   return PCQ_OK;
@@ -1360,7 +1492,7 @@ int pcq_collector_reset(pcq_collector* c) {
   c->pass_mode = 0;
   c->rawlog_len = 0;
   c->own_parts = c->own_me = 0;
-  if (c->kind == PCQ_COLLECT_GRID) {
+  if (c->kind == PCQ_COLLECT_GRID && c->grid.table) {  // (a sub-box table is kept: ensure_grid_tables checks the next box)
     CU(cudaMemsetAsync(c->grid.table, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
     if (c->grid.hkeys) CU(cudaMemsetAsync(c->grid.hkeys, 0xFF, c->grid.table_slots * 8ull, ctx->stream));
   }
@@ -1535,6 +1667,7 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
   std::vector<Segment> segs;
   segs.reserve(n_files);
   std::vector<uint64_t> lane_points(n_collectors, 0);
+  LaneBoxes lane_box(n_collectors);
   bool frac_known = true;
   double frac_pts = 0.0, all_pts = 0.0;
   pcq_scan_stats st{};
@@ -1544,6 +1677,7 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
     if (!f) return fail(PCQ_ERR_ARG, "null file %u", i);
     if (f->ctx != ctx) return fail(PCQ_ERR_ARG, "file %u belongs to another context", i);
     const uint32_t lane = n_collectors == 1 ? 0 : i;
+    lane_box.add(lane, f->desc);
     pcq_collector* c = collectors[lane];
     const uint64_t base = f->has_scan_base ? f->scan_base : c->scan_total;
     if (!f->has_scan_base) c->scan_total += f->n_points;
@@ -1603,8 +1737,9 @@ int pcq_search_files(pcq_ctx* ctx, pcq_file* const* files, uint32_t n_files, con
   st.points_scanned = (uint64_t)all_pts;
   st.segments = (uint32_t)segs.size();
   ctx->stats = st;
+  lane_box.cut(query);
   return run_batch(ctx, segs, query, collectors, n_collectors, lane_points,
-                   frac_known && all_pts > 0.0 ? std::min(1.0, frac_pts / all_pts) : -1.0);
+                   frac_known && all_pts > 0.0 ? std::min(1.0, frac_pts / all_pts) : -1.0, &lane_box.v);
 }
 
 int pcq_host_alloc(size_t n_bytes, void** out) {
@@ -2067,6 +2202,12 @@ int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t*
   for (size_t j = 0; j < std::min(prefetch, pieces.size()); ++j) RC(issue_copy(j));
   std::vector<Segment> segs;
   std::vector<uint64_t> lane_points(n_collectors, 0);
+  std::vector<LaneBoxes> lane_boxes;  // per query: every file of the call on its lane
+  for (uint32_t q = 0; q < n_queries; ++q) {
+    lane_boxes.emplace_back(n_collectors);
+    for (uint32_t i = 0; i < n_files; ++i) lane_boxes.back().add(fps[i].lane, fps[i].d);
+    lane_boxes.back().cut(queries + q);
+  }
   for (size_t j = 0; j < pieces.size(); ++j) {
     if (j + prefetch < pieces.size()) RC(issue_copy(j + prefetch));
     const Piece& pc = pieces[j];
@@ -2086,7 +2227,7 @@ int search_host_multi(pcq_ctx* ctx, const void* const* file_bytes, const size_t*
       // run_batch indexes lanes by Segment::lane, so hand it the query's full collector array
       const double fr = expected_match_fraction(fp.d, queries + q);
       RC(run_batch(ctx, segs, queries + q, collectors + (size_t)q * n_collectors, n_collectors, lane_points,
-                   fr < 0.0 ? fr : std::min(1.0, fr / fp.kept_fraction)));
+                   fr < 0.0 ? fr : std::min(1.0, fr / fp.kept_fraction), &lane_boxes[q].v));
     }
     if (fp.build_box || fp.build_cls) {
       // chunk headers as a by-product: the piece is resident anyway (unfiltered files travel as one run per piece,
@@ -2254,6 +2395,7 @@ int pcq_grid_import_candidates(pcq_collector* c, const void* dev_candidates, uin
   if (!dev_candidates) return fail(PCQ_ERR_ARG, "null candidates");
   pcq_ctx* ctx = c->ctx;
   RC(use_device(ctx));
+  RC(ensure_grid_tables(&c, 1, nullptr));
   RC(grid_restore(c));
   c->final_valid = false;
   for (int attempt = 0; attempt < 8; ++attempt) {

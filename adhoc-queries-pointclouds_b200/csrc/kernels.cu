@@ -374,7 +374,18 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
 
 // find-or-insert the slot of `key`.  dense: slot == key.  hashed: linear probing on hkeys.
 __device__ __forceinline__ uint64_t grid_slot(const GridDev& g, uint64_t key, bool insert) {
-  if (g.hkeys == nullptr) return key;
+  if (g.hkeys == nullptr) {
+    if (!g.sub_on) return key;  // dense over the whole grid: slot == key
+    // Dense over a sub-box: a collector that is fed by one file (run_search_parallel makes one grid per file,
+    // main.rs:253-273) only ever sees the cells under that file's header box — a 64th of the doc grid — so its table
+    // covers those cells only.  A cell outside (a header that lies about its bounds) reports "no slot": the host then
+    // moves the collector to a table over the whole grid and runs the launch again (rehash_grid).
+    const uint64_t dx = (key & g.mask[0]) - g.sub_lo[0];
+    const uint64_t dy = ((key >> g.shift_y) & g.mask[1]) - g.sub_lo[1];
+    const uint64_t dz = (key >> g.shift_z) - g.sub_lo[2];
+    if (dx >= g.sub_n[0] || dy >= g.sub_n[1] || dz >= g.sub_n[2]) return ~0ull;
+    return dx + g.sub_n[0] * (dy + g.sub_n[1] * dz);
+  }
   const uint64_t mask = g.table_slots - 1ull;
   uint64_t s = mix64(key) & mask;
   for (uint64_t probe = 0; probe < g.table_slots; ++probe) {
@@ -2262,7 +2273,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select_bytes(ScanParams P) {
       // ... and the class bytes of the unit after that are asked into L2 (one 128-byte line per lane), if the
       // dispatcher has described it already: a warp's eight loads are issued back to back and return together, so
       // without this a warp has 4 KB in flight for one DRAM latency per unit and nothing while it counts.
-      if (nxt) {
+      if (nxt) {  // (two units ahead; three or four measured the same)
         const uint32_t nb2 = (n + 2u) % kSelBufs;
         if (mbar_test(&bar_tk[nb2], ((n + 2u) / kSelBufs) & 1u) && unit[nb2].tile != ~0ull) {
           const uint32_t off = w * (uint32_t)kSelBWarpPts + ln * 128u;

@@ -79,6 +79,12 @@ struct GridDev {
   uint32_t log_only;     // 1: second pass of a launch that met new affected keys — log their points, insert nothing
   uint32_t own_parts;    // finalisation: > 1 = only cells with mix64(key) % own_parts == own_me are finalists (multi-GPU owner)
   uint32_t own_me;
+  // dense table over a sub-box of the grid (kernels.cu grid_slot): cells [sub_lo, sub_lo + sub_n) per axis, x fastest
+  uint32_t sub_on;
+  uint32_t pad_;
+  uint64_t sub_lo[3];
+  uint64_t sub_n[3];
+  uint32_t pad2_;
   uint32_t fast_div;     // 1: every axis extent is a normal number in [2^-500, 2^500] — division by reciprocal (grid_math.cuh)
   double ext[3];         // bmax - bmin, the divisor of :51-57
   double inv_ext[3];     // RN(1 / ext), IEEE division on the host

@@ -140,6 +140,7 @@ struct pcq_collector {
   uint8_t* d_final = nullptr;
   uint64_t final_cap = 0, final_n = 0;
   bool final_valid = false;
+  uint64_t total_bits = 0;           // GRID: key bits (bits.x + bits.y + bits.z)
   bool table_holds_winners = false;  // finalised in place: the cells of the winners hold scan indices until grid_restore
   // key-aliasing replay (alias.cu): affected keys in ordinal order, their fold states (host copy is authoritative
   // between launches), the device-side set and the replay log
@@ -187,6 +188,7 @@ int upload(pcq_ctx* ctx, const void* src, size_t bytes, void** dev_out);
 int upload2(pcq_ctx* ctx, const void* a, size_t na, const void* b, size_t nb, void** dev_a, void** dev_b);
 GridDev grid_view(const pcq_collector* c);
 int grid_restore(pcq_collector* c);
+int ensure_grid_tables(pcq_collector* const* cols, uint32_t n, const double* boxes);
 int grow_log(pcq_collector* c, uint64_t need);
 int alias_upload(pcq_collector* c);
 int grid_finalize(pcq_collector* c);

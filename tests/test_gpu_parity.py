@@ -743,3 +743,48 @@ def test_batched_collector_reset(pcq, ctx):
         assert [c.point_count() for c in cols] == [0] * len(cols)
         pcq.BoundsSearcher(*box2).search_files(images, _impl(pcq), cols)
         assert_same(kind, cols, oracle_run(files, exts, kind, bounds=box2, grid=grid, per_file=True))
+
+
+def test_many_per_file_grids_share_the_hbm(pcq, ctx):
+    """`query --parallel --density` makes one grid per file (main.rs:253-273).  A 2^30-cell grid is an 8 GB dense table:
+    twelve of them must not be allocated side by side — the tables are sized when the collectors are first used, by how
+    many of them the call brings (ensure_grid_tables), and the result does not depend on dense or hashed."""
+    rng = np.random.default_rng(77)
+    n_files = 12
+    files = [make_file(rng.integers(0, 1_000_000, size=(3000, 3)), rng.integers(1, 4, size=3000), fmt=1, seed=k) for k in range(n_files)]
+    exts = ["las"] * n_files
+    box = ((0.0, 0.0, 0.0), (10_000.0, 10_000.0, 10_000.0))
+    grid = (box[0], box[1], 10.0)  # 1000^3 cells: 10 + 10 + 10 key bits
+    got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_GRID, bounds=box, grid=grid, per_file=True)
+    want = oracle_run(files, exts, orc.COLLECT_GRID, bounds=box, grid=grid, per_file=True)
+    assert_same(orc.COLLECT_GRID, got, want)
+
+
+def test_per_file_grid_tables_cover_the_file_box_and_fall_back(pcq, ctx):
+    """A per-file grid's table covers only the cells under the file's header box (cut by the query box).  A header that
+    understates its bounds sends points outside that sub-box: the collector moves to a table over the whole grid and the
+    launch runs again — the result is the oracle's either way, resident and host-streamed, and after a reset."""
+    rng = np.random.default_rng(91)
+    files, exts = [], []
+    for k in range(6):
+        lo = np.array([k * 150_000, 0, 0])
+        xyz = lo + rng.integers(0, 150_000, size=(4000, 3))
+        honest = dict()
+        if k % 2 == 1:  # lying header: claims a tenth of the real extent (still intersects the query)
+            honest = dict(hdr_min=(lo[0] * 0.01, 0.0, 0.0), hdr_max=(lo[0] * 0.01 + 150.0, 150.0, 150.0))
+        files.append(make_file(xyz, rng.integers(1, 4, size=4000), fmt=3 if k % 3 == 0 else 1, seed=k, **honest))
+        exts.append("las")
+    box = ((0.0, 0.0, 0.0), (9000.0, 1500.0, 1500.0))
+    grid = (box[0], box[1], 5.0)  # 1800 x 300 x 300 cells (11 + 9 + 9 key bits); a file's honest box is 300^3 of them
+    want = oracle_run(files, exts, orc.COLLECT_GRID, bounds=box, grid=grid, per_file=True)
+    for host_stream in (False, True):
+        got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_GRID, bounds=box, grid=grid, per_file=True, host_stream=host_stream)
+        assert_same(orc.COLLECT_GRID, got, want)
+        # the same collectors again after a reset, fed the files in reverse: other boxes than the tables were made for
+        pcq.reset_collectors(got)
+        searcher = pcq.BoundsSearcher(*box)
+        searcher.search_files(list(zip(files[::-1], exts)), _impl(pcq), got)
+        assert_same(orc.COLLECT_GRID, got, want[::-1])
+    # one grid over all files (run_search_sequential): the box is the union of the header boxes
+    got = gpu_run(pcq, ctx, files, exts, orc.COLLECT_GRID, bounds=box, grid=grid)
+    assert_same(orc.COLLECT_GRID, got, oracle_run(files, exts, orc.COLLECT_GRID, bounds=box, grid=grid))

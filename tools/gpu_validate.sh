@@ -1,0 +1,19 @@
+#!/bin/bash
+# full GPU suite, select probes, full N = 1 bench (run under gpurun)
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/gpu_tests.log
+tail -4 gpurun_out/gpu_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+{ for c in 6 19 2; do python tools/grid_probe.py lastsel $c 7; done; } > gpurun_out/lastsel.txt 2>&1; cat gpurun_out/lastsel.txt
+python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
+tail -c 1500 gpurun_out/bench_n1.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['frac'])
+e=d['e2e']; print('e2e', e['value'], 'last', e['as_last_columns']['value'])
+print('indexed', json.dumps(e['strip_ordered_indexed_repeat'])[:1800])
+print('cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
+for k,q in d['density']['queries'].items(): print(k, q['ms_end_to_end_host_clock'], q['phases']['scan_ms'], q['phases']['finalize_ms'], q['equals_oracle'])
+for r in d['extra']: print(r['config'], r['query'], r['collector'], round(r['ms'],3), round(r['frac'],3), r.get('finalize_ms_host_clock'))
+PY
