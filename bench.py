@@ -131,6 +131,13 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            # the first call of each query refreshes NVML's cached state and takes 7-26 ms (measured, tools/nvml_cost.py;
+            # later calls ~1 us): made here, before the thread and the timed region start
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons"):
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            else:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
 
             def loop():
                 while not self.stop_flag.is_set():
@@ -477,8 +484,8 @@ def main():
         res = device_step()
     per_file_counts = [r.counts() for r in res]
     sampler = ClockSampler(local_rank)
+    sampler.start()  # (primes NVML, then samples every 5 ms; the idle samples before the barrier fall out of the median)
     barrier()
-    sampler.start()
     launches0 = group.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
