@@ -169,7 +169,11 @@ void pcq_file_release(pcq_file* f);
 /* ---- collectors -------------------------------------------------------------------------------- */
 
 /* kind = PCQ_COLLECT_GRID uses gmin/gmax/cell_size exactly as GridSampledCollector::new(bounds,
- * cell_size) (collect_points.rs:104-108; main.rs:253-264); other kinds ignore them (may be NULL). */
+ * cell_size) (collect_points.rs:104-108; main.rs:253-264); other kinds ignore them (may be NULL).
+ * A grid collector's cell table is allocated by the first search that feeds it, out of a third of the free HBM shared
+ * by the grid collectors of that call, and covers the cells under the header boxes of the collector's files (cut by the
+ * query box) when that is much less than the whole grid — creating 64 per-file collectors costs nothing until they
+ * are used, and a file whose header understates its bounds only costs a second launch. */
 int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const double gmax[3],
                          double cell_size, pcq_collector** out);
 void pcq_collector_destroy(pcq_collector* c);
