@@ -153,6 +153,7 @@ def _load() -> C.CDLL:
         "pcq_collector_destroy": (None, [vp]),
         "pcq_collector_reset": (C.c_int, [vp]),
         "pcq_collectors_reset": (C.c_int, [P(vp), u32]),
+        "pcq_grid_cells_under_box": (C.c_int, [_D3, _D3, C.c_double, _D3, _D3, u64 * 3, u64 * 3]),
         "pcq_collector_point_count": (C.c_int, [vp, P(u64)]),
         "pcq_collector_points": (C.c_int, [vp, P(vp), P(u64)]),
         "pcq_collector_points_device": (C.c_int, [vp, P(vp), P(u64)]),

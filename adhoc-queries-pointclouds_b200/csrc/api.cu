@@ -1499,6 +1499,28 @@ int pcq_collector_reset(pcq_collector* c) {
   return PCQ_OK;
 }
 
+int pcq_grid_cells_under_box(const double gmin[3], const double gmax[3], double cell_size, const double box_min[3],
+                             const double box_max[3], uint64_t lo[3], uint64_t n[3]) {
+  if (!gmin || !gmax || !box_min || !box_max || !lo || !n) return fail(PCQ_ERR_ARG, "null argument");
+  uint64_t dims[3], bits[3];
+  RC(grid_params(gmin, gmax, cell_size, dims, bits));
+  GridDev g{};
+  for (int a = 0; a < 3; ++a) {
+    if (bits[a] > 62) return fail(PCQ_ERR_GRID, "SparseGrid axis with %llu key bits is not representable", (unsigned long long)bits[a]);
+    g.bmin[a] = gmin[a];
+    g.bmax[a] = gmax[a];
+    g.dims_f[a] = (double)dims[a];
+    g.ext[a] = gmax[a] - gmin[a];
+    g.mask[a] = (1ull << bits[a]) - 1ull;
+  }
+  for (int a = 0; a < 3; ++a)
+    if (!cell_range(g, a, box_min[a], box_max[a], &lo[a], &n[a])) {  // no usable range on this axis: every cell
+      lo[a] = 0;
+      n[a] = g.mask[a] + 1ull;
+    }
+  return PCQ_OK;
+}
+
 int pcq_collectors_reset(pcq_collector* const* collectors, uint32_t n) {
   if (!collectors && n) return fail(PCQ_ERR_ARG, "null collectors");
   std::vector<pcq_collector*> rest;

@@ -179,6 +179,14 @@ int pcq_collector_create(pcq_ctx* ctx, int kind, const double gmin[3], const dou
 void pcq_collector_destroy(pcq_collector* c);
 /* Forget everything collected so far (keeps allocations). */
 int pcq_collector_reset(pcq_collector* c);
+/* Host only (no GPU needed): the cells of SparseGrid(gmin, gmax, cell_size) that positions inside the box
+ * [box_min, box_max] can fall into — per axis the first cell lo[a] and the number of cells n[a] (one cell of margin on
+ * both sides, clamped to the axis' key mask).  This is the sub-box a grid collector's dense table is made for when it
+ * is fed files whose header boxes (cut by the query box) lie inside the box; every position p with box_min <= p <=
+ * box_max has lo[a] <= cell_a(p) < lo[a] + n[a] unless the cell exceeds the mask (such points are aliased and bypass
+ * the table, grid_sampling.rs:62-70). */
+int pcq_grid_cells_under_box(const double gmin[3], const double gmax[3], double cell_size, const double box_min[3],
+                             const double box_max[3], uint64_t lo[3], uint64_t n[3]);
 /* pcq_collector_reset for a list of collectors (e.g. the per-file collectors of run_search_parallel before the next
  * query): the count and buffer collectors of a context are cleared by ONE kernel launch instead of one stream operation
  * each; grid collectors are reset one by one. */

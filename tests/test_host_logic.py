@@ -12,6 +12,9 @@ import pytest
 
 from oracle import np_oracle as npo
 from oracle import oracle as orc
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
 from tests.helpers import make_file
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -342,3 +345,43 @@ def test_index_filter_property_random_boxes(pcq):
     with pytest.raises(pcq.PcqError) as e:
         pcq.index_filter(headers, desc, pcq.BoundsSearcher(qmin, qmax))
     assert e.value.code == pcq.binding.PCQ_ERR_PANIC
+
+
+# ---- the sub-box a per-file grid's table covers (pcq_grid_cells_under_box) ---------------------------------------------
+@settings(max_examples=150, deadline=None, derandomize=True)
+@given(st.tuples(st.floats(-1e5, 1e5), st.floats(-1e5, 1e5), st.floats(-1e3, 1e3)),
+       st.tuples(st.floats(0.5, 5e4), st.floats(0.5, 5e4), st.floats(0.5, 2e3)),
+       st.sampled_from([0.01, 0.1, 0.37, 1.0, 25.0, 100.0]),
+       st.tuples(st.floats(-0.3, 1.2), st.floats(-0.3, 1.2), st.floats(-0.3, 1.2)),
+       st.tuples(st.floats(0.0, 0.8), st.floats(0.0, 0.8), st.floats(0.0, 0.8)),
+       st.integers(0, 2**31 - 1))
+def test_cells_under_a_box_hold_every_position_of_the_box(pcq, gmin, ext, cell, rel_lo, rel_len, seed):
+    """Soundness of the table sizing: a position inside the box falls into a cell of the reported range on every axis,
+    unless the cell exceeds the axis' key mask (aliased: such points bypass the table).  Cells as the numpy restatement
+    of SparseGrid computes them (grid_sampling.rs:51-60)."""
+    from oracle import np_oracle
+
+    gmax = tuple(gmin[a] + ext[a] for a in range(3))
+    try:
+        grid = np_oracle.SparseGrid(gmin, gmax, cell)
+    except ValueError:
+        return
+    if any(b > 62 for b in grid.bits):
+        return
+    box_min = tuple(gmin[a] + rel_lo[a] * ext[a] for a in range(3))
+    box_max = tuple(box_min[a] + rel_len[a] * ext[a] for a in range(3))
+    B = pcq.binding
+    lo, n = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+    B.check(B.lib.pcq_grid_cells_under_box(B.d3(gmin), B.d3(gmax), float(cell), B.d3(box_min), B.d3(box_max), lo, n))
+    rng = np.random.default_rng(seed)
+    pts = [box_min, box_max] + [tuple(box_min[a] + rng.random() * (box_max[a] - box_min[a]) for a in range(3)) for _ in range(40)]
+    for p in pts:
+        c = grid._cell(p)
+        for a in range(3):
+            if c[a] > (1 << grid.bits[a]) - 1:
+                continue
+            assert lo[a] <= c[a] < lo[a] + n[a], (a, p, c, list(lo), list(n))
+    # a box that covers a small part of the grid gets a small range
+    for a in range(3):
+        if 0.0 <= rel_lo[a] and rel_lo[a] + rel_len[a] <= 1.0 and grid.dims[a] > 0:
+            assert n[a] <= rel_len[a] * grid.dims[a] + 4
