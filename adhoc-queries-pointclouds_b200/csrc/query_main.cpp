@@ -174,7 +174,28 @@ int main(int argc, char** argv) {
     const double t_args = since_start();
     const SearchImplementation impl = optimized ? SearchImplementation::Optimized : SearchImplementation::Regular;
     double t_ctx = 0.0;
-    if (gpus > 1) {
+    // A bounds query whose box touches no file's header box finds nothing in any file — every search returns before
+    // its per-point loop (`if !file_bounds.intersects(&bounds) { return Ok(()) }`, las.rs:82-84, last.rs:92-94).  That
+    // is header work: no device context (seconds on these boxes) is created for it.  Anything that could make the
+    // normal path fail (another extension, an unreadable header) goes the normal path.
+    bool nothing_to_scan = optimized && bounds != nullptr;
+    for (size_t i = 0; i < input_files.size() && nothing_to_scan; ++i) {
+      MappedFile m(input_files[i]);
+      const std::string ext = m.extension();
+      pcq_file_desc d;
+      int hit = 1;
+      if ((ext != "las" && ext != "last") ||
+          pcq_parse_header(m.data(), m.size(), ext == "last" ? PCQ_LAYOUT_LAST : PCQ_LAYOUT_LAS, 0, &d) != PCQ_OK ||
+          pcq_file_intersects(&d, bounds->min, bounds->max, &hit) != PCQ_OK || hit)
+        nothing_to_scan = false;
+    }
+    if (nothing_to_scan) {
+      t_ctx = since_start();
+      std::printf("Searching %zu files...\n", input_files.size());
+      // CountCollector: "Found 0 matching points"; Buffer / GridSampled collectors hand the dumper empty slices, which
+      // writes nothing and prints nothing (main.rs:134-143, dump_points.rs:65-67)
+      if (!have_density && !have_output) std::printf("Found 0 matching points\n");
+    } else if (gpus > 1) {
       // ---- a group of GPUs: every file is cut into point ranges, one per GPU; each GPU streams its ranges over its
       // own PCIe link; counts are summed on the host, selected records concatenated in scan order, density cells
       // exchanged by owner (group.cu).  Same collectors, same output rules.

@@ -62,6 +62,32 @@ def _read_las_fmt2(path: Path):
     return n, np.array(scale), np.array(offset), xyz, rec[:, 15].copy(), np.ascontiguousarray(rec[:, 20:26]).view("<u2").reshape(n, 3)
 
 
+@pytest.mark.parametrize("ext", ["las", "last"])
+def test_cli_box_that_touches_no_file_needs_no_gpu(pcq, tmp_path, ext):
+    """Every search returns before its per-point loop when the file's header box does not intersect the query box
+    (las.rs:82-84, last.rs:92-94): the CLI answers such a query from the headers, with the reference's lines."""
+    d = tmp_path / "data"
+    d.mkdir()
+    files = _dataset(pcq, d, ext)
+    far = "0;0;0;10;10;10"
+    assert orc.count_parallel(files, [ext] * 4, 4, bounds=((0, 0, 0), (10, 10, 10))).sum() == 0
+    for flags in (["--parallel"], []):
+        r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", far, "--optimized", *flags], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().splitlines()
+        assert lines[0] == "Searching 4 files..." and lines[1] == "Found 0 matching points"
+        assert re.match(r"Searched \d+\.\d\d MiB in \d+\.\d\ds \(throughput: \d+\.\d\dMiB/s\)", lines[-1])
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", far, "--optimized", "--parallel", "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Found" not in r.stdout and "Writing" not in r.stdout and not list(out.iterdir())
+    r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", far, "--optimized", "--density", "1.0"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Found" not in r.stdout
+    # the refusal of the Regular implementation comes first
+    r = subprocess.run([str(QUERY), "-i", str(d), "--bounds", far], capture_output=True, text=True)
+    assert r.returncode == 1 and ("Regular" in r.stderr or "CUDA" in r.stderr)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ext", ["las", "last"])
 def test_cli_matches_oracle(pcq, tmp_path, ext):
