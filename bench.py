@@ -963,7 +963,11 @@ def extra_records(pcq, ctx, stream, peak):
             s.search_files(dfs, impl, bcols)
 
         ms = timed(runb, reps=3)
-        rec("C3 ca13 LAST 64 x 40.75M", f"class {klass}", "buffer (compacted 31-byte records)", total, matches, total + matches * (12 + 31), ms)
+        # SURVEY §8d counts the gathered positions of a sparse select "at 32-byte sector granularity": a 12-byte position
+        # at a 4-byte phase lies in 1.25 sectors on average (40 bytes), and no more than the whole column can be read
+        sector_bytes = total + min(matches * 40, total * 12) + matches * 31
+        rec("C3 ca13 LAST 64 x 40.75M", f"class {klass}", "buffer (compacted 31-byte records)", total, matches, total + matches * (12 + 31), ms,
+            algorithmic_bytes_sector_granularity=int(sector_bytes), frac_sector_granularity=sector_bytes / ms / 1e6 / peak)
         for b in bcols:
             b.close()
         torch.cuda.empty_cache()
